@@ -1,0 +1,132 @@
+/* fcest_b200 -- C ABI of the B200-native (sm_100a) hot path of OnnoKampman/FCEst.
+ *
+ * Drop-in boundary.  The reference has no FFI of its own: its "plugin API" is the GPflow subclassing
+ * contract.  Each entry point below names the reference code it replaces
+ * (paths relative to the reference checkout); INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.  Conventions:
+ *   - all pointers are DEVICE pointers to float64 row-major data owned by the caller; no entry point
+ *     allocates, synchronises the device or touches the host (workspaces are caller supplied);
+ *   - `stream` is a cudaStream_t passed as void*-compatible handle; work is enqueued on it;
+ *   - return value: 0 on success, a cudaError_t value (> 0) if a launch failed, or a negative
+ *     FCEST_ERR_* code for argument errors;
+ *   - numerical failure of a Cholesky factorisation is reported LAPACK-style through a device
+ *     `int info[]` (0 = ok, k = first non-positive pivot, 1-based), mirroring the
+ *     InvalidArgumentError TensorFlow raises at fcest/models/likelihoods.py:184-189;
+ *   - operands of fcest_dgemm must be 16-byte aligned with even leading dimensions.
+ */
+#ifndef FCEST_B200_H_
+#define FCEST_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDACC__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define FCEST_ERR_ALIGNMENT (-1)
+#define FCEST_ERR_UNSUPPORTED (-2)
+#define FCEST_ERR_ARGUMENT (-3)
+
+/* ---- likelihood: fcest/models/likelihoods.py:93-206 (variational_expectations + _log_prob) and the
+ *      TF autodiff of it (fcest/helpers/inference.py:113-116).  One call = forward and, when g_fmean
+ *      is non-null, the fused analytic backward.
+ *   fmean, fvar : (N, R=D*nu) with row pitch ldf;  eps : (S, N, R) contiguous N(0,1) draws
+ *   y : (N, D);  A : a_mode 0 -> (D, nu) matrix, 1 -> (nu,) vector; applied as a Hadamard product
+ *   lam : (D,) unconstrained additive noise (softplus applied inside, likelihoods.py:253-264)
+ *   ve : (N,) out, mean over samples of the Gaussian log density
+ *   g_fmean, g_fvar : (N, R) pitch ldg, d sum(ve) / d fmean, fvar;  gA : (D,nu) or (nu,);  glam : (D,)
+ *   ws_gA_part : (N, R) and ws_glam_part : (N, D) workspaces;  info : (N,) */
+long long fcest_wishart_loglik_smem_bytes(int D, int nu);
+int fcest_wishart_loglik(const double* fmean, const double* fvar, long long ldf, const double* eps,
+                         const double* y, const double* A, int a_mode, const double* lam, int S,
+                         int N, int D, int nu, double* ve, double* g_fmean, double* g_fvar,
+                         long long ldg, double* gA, double* glam, double* ws_gA_part,
+                         double* ws_glam_part, int* info, cudaStream_t stream);
+
+/* ---- fp64 tensor-core GEMM (DMMA): C = alpha op(A) op(B) + beta C + bias_row[m] + bias_col[n].
+ *      Replaces the tf.matmul calls inside gpflow.conditionals.util.base_conditional that
+ *      SVGP.elbo / VGP.elbo / predict_f reach from fcest/models/wishart_process.py:109-114,381-386.
+ *   a_kmajor: A[m*lda+k] else A[k*lda+m];  b_kmajor: B[n*ldb+k] else B[k*ldb+n];  batch via strides. */
+long long fcest_dgemm_workspace_bytes(int M, int N, int K, long long ldc, int batch);
+int fcest_dgemm(int a_kmajor, int b_kmajor, int M, int N, int K, double alpha, const double* A,
+                long long lda, long long strideA, const double* B, long long ldb, long long strideB,
+                double beta, double* C, long long ldc, long long strideC, const double* bias_row,
+                const double* bias_col, int batch, double* workspace, long long workspace_bytes,
+                cudaStream_t stream);
+
+/* ---- packed quadratic-form projection (replaces the (R,M,N) LTA tensor of base_conditional and its
+ *      autodiff).  K = M(M+1)/2 packed lower-triangle entries, row pitch ldk >= K, even.
+ *   pack_outer : Pk[n,(i,j)] = w_ij P[i,n] P[j,n];  bias[n] = use_prior ? kvar - sum_m P[m,n]^2 : 0
+ *   tri_syrk_pack : Sk[r,(i,j)] = (tril(q_sqrt_r) tril(q_sqrt_r)^T)[i,j];  kl_parts[r] = {tr S_r, sum log L_mm^2}
+ *   tri_grad : dq_sqrt_r = tril(2 W_r L_r - kl L_r) + kl diag(1/L_mm),  W_r from Gk = g_var^T Pk
+ *   sym_matvec : dP[:,n] (+)= 2 T_n p_n - use_prior * 2 gs[n] p_n,  T_n from Tk = g_var Sk */
+int fcest_pack_outer(const double* P, long long ldp, int M, int N, double* Pk, long long ldk,
+                     double* bias, const double* kvar, int use_prior, cudaStream_t stream);
+int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* Sk, long long ldk,
+                        double* kl_parts, cudaStream_t stream);
+int fcest_tri_grad(const double* Gk, long long ldk, const double* q_sqrt, int R, int M,
+                   double* dq_sqrt, double kl, cudaStream_t stream);
+int fcest_sym_matvec(const double* Tk, long long ldk, const double* P, long long ldp, int M, int N,
+                     const double* g_var, long long ldg, int R, int use_prior, double* dP,
+                     long long lddp, double* gs_out, int accumulate, cudaStream_t stream);
+
+/* ---- gpflow.kernels.Matern52 (default kernel, fcest/models/wishart_process.py:99-100,326) and its
+ *      adjoint; kvar / kls are device scalars holding the constrained variance and lengthscale. */
+int fcest_matern52(const double* X1, int n1, const double* X2, int n2, int dim, const double* kvar,
+                   const double* kls, double jitter, double* K, long long ldk, cudaStream_t stream);
+int fcest_matern52_bwd(const double* X1, int n1, const double* X2, int n2, int dim,
+                       const double* kvar, const double* kls, const double* gK, long long ldg,
+                       int sym, double* ws_part, double* g_var, double* g_ls, double* gX1,
+                       int accumulate, cudaStream_t stream);
+
+/* ---- tf.linalg.cholesky / triangular_solve on the single M x M kernel matrix (base_conditional). */
+int fcest_chol_single(double* A, int M, long long lda, int* info, cudaStream_t stream);
+int fcest_tri_inv_single(const double* L, int M, long long ldl, double* Li, long long ldi,
+                         cudaStream_t stream);
+
+/* ---- glue: masks, transposes, axpby, deterministic reductions, softplus transforms. */
+int fcest_tril(double* X, int M, long long ld, int mode, cudaStream_t stream);
+int fcest_transpose(const double* X, int rows, int cols, long long ldx, double* Y, long long ldy,
+                    cudaStream_t stream);
+int fcest_axpby(long long n, double a, const double* x, double b, double* y, cudaStream_t stream);
+int fcest_sum(const double* x, long long n, long long stride, double scale, double* out,
+              int accumulate, cudaStream_t stream);
+int fcest_sumsq(const double* x, int rows, int cols, long long ld, double scale, double* out,
+                int accumulate, cudaStream_t stream);
+int fcest_softplus_fwd(const double* u, double* out, int n, cudaStream_t stream);
+int fcest_softplus_bwd(const double* u, const double* g_c, double* g_u, int n, cudaStream_t stream);
+
+/* ---- tf.optimizers.Adam(learning_rate=1e-3) as applied by run_adam
+ *      (fcest/helpers/inference.py:72-74,111-116); t is the 1-based step, grad_sign = -1 for an ELBO. */
+int fcest_adam_step(double* theta, const double* grad, double* m, double* v, long long n,
+                    double grad_sign, long long t, double lr, double b1, double b2, double eps,
+                    cudaStream_t stream);
+
+/* ---- tf.random.normal stand-in (likelihoods.py:130-134, wishart_process.py:200-204,491-495):
+ *      Philox4x32-10 + Box-Muller, counter based (element index, offset), keyed by seed. */
+int fcest_randn(double* out, long long n, unsigned long long seed, unsigned long long offset,
+                cudaStream_t stream);
+
+/* ---- prediction: _get_cov_samples + predict_cov / predict_corr
+ *      (fcest/models/wishart_process.py:120-212, :392-504; helpers/array_operations.py:56-103).
+ *   cov_moments streams Sc samples Sigma = (A o F)(A o F)^T + diag(softplus(lam)) (optionally converted
+ *   to correlations) into a running Welford state (mean, m2: (N,D,D), cnt0 samples already folded);
+ *   `samples` (Sc,N,D,D) optionally receives the raw samples; finalize writes mean and population std.
+ *   batched_chol_info: the are_all_positive_definite() assertion: -1 = not symmetric, k>0 = not PD. */
+int fcest_cov_moments(const double* fmean, const double* fvar, long long ldf, const double* eps,
+                      const double* A, int a_mode, const double* lam, int Sc, int N, int D, int nu,
+                      int corr, long long cnt0, double* mean, double* m2, double* samples,
+                      int finalize, double* out_mean, double* out_std, cudaStream_t stream);
+int fcest_batched_chol_info(const double* A, int B, int D, double atol, int* info,
+                            cudaStream_t stream);
+
+/* ---- instrumentation: number of kernels this library has launched since load (bench.py "gpu_launches"). */
+long long fcest_launch_count(void);
+long long fcest_launch_count_add(long long n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCEST_B200_H_ */
