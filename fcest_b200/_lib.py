@@ -94,11 +94,25 @@ _ERR = {-1: "operand alignment (16-byte pointers, even leading dimensions)", -2:
         -3: "bad argument"}
 
 
-def call(name: str, *args):
+# Optional per-call device timing (bench.py): {"min_flops": f, "records": [(name, flops, ev0, ev1)]}.
+# CUDA events are recorded on the launching stream around the C call; nothing is synchronised here.
+PROFILE = None
+
+
+def call(name: str, *args, flops: float = 0.0):
     """Invoke an ``int``-returning entry point on the current stream and raise on a non-zero status."""
     require_cuda()
     fn = getattr(load_library(), name)
-    rc = fn(*args, stream())
+    prof = PROFILE
+    if prof is not None and flops >= prof["min_flops"]:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*args, stream())
+        ev1.record()
+        prof["records"].append((name, flops, ev0, ev1))
+    else:
+        rc = fn(*args, stream())
     if rc != 0:
         what = _ERR.get(rc, f"CUDA error {rc}")
         raise RuntimeError(f"{name} failed: {what}")

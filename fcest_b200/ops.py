@@ -58,7 +58,7 @@ def dgemm(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C, alpha
     ws = _workspace(nbytes, C.device) if nbytes else None
     call("fcest_dgemm", int(a_kmajor), int(b_kmajor), M, N, K, float(alpha), ptr(A), ld(A), 0, ptr(B),
          ld(B), 0, float(beta), ptr(C), ld(C), 0, ptr(bias_row), ptr(bias_col), 1, ptr(ws),
-         ws.numel() * 8 if ws is not None else 0)
+         ws.numel() * 8 if ws is not None else 0, flops=2.0 * M * N * K)
     return C
 
 
@@ -155,7 +155,7 @@ def wishart_loglik(fmean, fvar, eps, y, A, lam, need_grad=True):
         ws_l = torch.empty((N, D), dtype=F64, device=dev)
         call("fcest_wishart_loglik", ptr(fmean), ptr(fvar), ld(fmean), ptr(eps), ptr(y), ptr(A), a_mode,
              ptr(lam), S, N, D, nu, ptr(ve), ptr(g_fmean), ptr(g_fvar), ld(g_fmean), ptr(gA), ptr(glam),
-             ptr(ws_a), ptr(ws_l), ptr(info))
+             ptr(ws_a), ptr(ws_l), ptr(info), flops=(3.0 * D * D * nu + 2.0 / 3.0 * D ** 3 + D * D) * S * N)
         out.update(g_fmean=g_fmean, g_fvar=g_fvar, gA=gA, glam=glam)
     else:
         call("fcest_wishart_loglik", ptr(fmean), ptr(fvar), ld(fmean), ptr(eps), ptr(y), ptr(A), a_mode,
