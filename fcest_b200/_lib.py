@@ -36,11 +36,12 @@ SIGNATURES = {
     "fcest_matern52_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _i, _p]),
     "fcest_chol_single": (_i, [_p, _i, _ll, _p, _p]),
     "fcest_tri_inv_single": (_i, [_p, _i, _ll, _p, _ll, _p]),
+    "fcest_chol_inv_single": (_i, [_p, _i, _ll, _p, _ll, _p, _p]),
     "fcest_tril": (_i, [_p, _i, _ll, _i, _p]),
     "fcest_transpose": (_i, [_p, _i, _i, _ll, _p, _ll, _p]),
     "fcest_axpby": (_i, [_ll, _d, _p, _d, _p, _p]),
     "fcest_sum": (_i, [_p, _ll, _ll, _d, _p, _i, _p]),
-    "fcest_sumsq": (_i, [_p, _i, _i, _ll, _d, _p, _i, _p]),
+    "fcest_sumsq": (_i, [_p, _i, _i, _ll, _d, _p, _i, _p, _p]),
     "fcest_softplus_fwd": (_i, [_p, _p, _i, _p]),
     "fcest_softplus_bwd": (_i, [_p, _p, _p, _i, _p]),
     "fcest_adam_step": (_i, [_p, _p, _p, _p, _ll, _d, _ll, _d, _d, _d, _d, _p]),

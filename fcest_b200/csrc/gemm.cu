@@ -45,12 +45,12 @@ template <int BMN, bool KMAJOR, int NTHREADS>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, long long ld,
                                           int mn0, int MN, int k0, int kend, int tid) {
   constexpr int CHUNKS = BMN * BK / 2;
-  constexpr int PER = CHUNKS / NTHREADS;
-  static_assert(CHUNKS % NTHREADS == 0, "tile/threads mismatch");
+  constexpr int PER = (CHUNKS + NTHREADS - 1) / NTHREADS;
   using L = TileLayout<BMN, KMAJOR>;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int c = tid + i * NTHREADS;
+    if (CHUNKS % NTHREADS != 0 && c >= CHUNKS) break;
     if (KMAJOR) {
       const int row = c >> 3, kc = (c & 7) * 2;
       const int gm = mn0 + row, gk = k0 + kc;
@@ -106,46 +106,64 @@ dgemm_dmma_kernel(const GemmParams p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  // Fragment loads for k4-step kk of the tile held in ring slot `slot`.
+  auto load_frags = [&](double (&a)[TM], double (&b)[TN], int slot, int kk) {
+    const double* a_s = sA + slot * LA::DOUBLES;
+    const double* b_s = sB + slot * LB::DOUBLES;
+    const int k = kk * 4 + tig;
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < ktiles) {
-      load_tile<BM, A_KMAJOR, NTHREADS>(sA + s * LA::DOUBLES, A, p.lda, m0, p.M, kbeg + s * BK, kend, tid);
-      load_tile<BN, B_KMAJOR, NTHREADS>(sB + s * LB::DOUBLES, B, p.ldb, n0, p.N, kbeg + s * BK, kend, tid);
+    for (int i = 0; i < TM; ++i) {
+      const int r = wm * WM + 8 * i + gid;
+      a[i] = A_KMAJOR ? a_s[r * LA::PITCH + k] : a_s[k * LA::PITCH + r];
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int c = wn * WN + 8 * j + gid;
+      b[j] = B_KMAJOR ? b_s[c * LB::PITCH + k] : b_s[k * LB::PITCH + c];
+    }
+  };
+  auto mma_step = [&](const double (&a)[TM], const double (&b)[TN]) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  };
+  auto issue_tile = [&](int t) {
+    if (t < ktiles) {
+      const int s = t % STAGES;
+      load_tile<BM, A_KMAJOR, NTHREADS>(sA + s * LA::DOUBLES, A, p.lda, m0, p.M, kbeg + t * BK, kend, tid);
+      load_tile<BN, B_KMAJOR, NTHREADS>(sB + s * LB::DOUBLES, B, p.ldb, n0, p.N, kbeg + t * BK, kend, tid);
     }
     cp_async_commit();
-  }
+  };
+
+  // Software pipeline: the ring holds tiles kt+1 .. kt+STAGES in flight while tile kt is consumed.
+  // The block barrier sits *before the last k4-step* of a tile, after that step's fragments are
+  // already in registers, so the first fragments of the next tile are fetched (LDS latency) and the
+  // barrier skew is absorbed underneath the last TM*TN DMMAs instead of stalling the tensor pipe.
+#pragma unroll
+  for (int s = 0; s < STAGES; ++s) issue_tile(s);
+  cp_async_wait<STAGES - 1>();
+  __syncthreads();
+  double fa[2][TM], fb[2][TN];
+  load_frags(fa[0], fb[0], 0, 0);
 
   for (int kt = 0; kt < ktiles; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < ktiles) {
-        const int s = nk % STAGES;
-        load_tile<BM, A_KMAJOR, NTHREADS>(sA + s * LA::DOUBLES, A, p.lda, m0, p.M, kbeg + nk * BK, kend, tid);
-        load_tile<BN, B_KMAJOR, NTHREADS>(sB + s * LB::DOUBLES, B, p.ldb, n0, p.N, kbeg + nk * BK, kend, tid);
-      }
-      cp_async_commit();
-    }
-    const double* a_s = sA + (kt % STAGES) * LA::DOUBLES;
-    const double* b_s = sB + (kt % STAGES) * LB::DOUBLES;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[TM], b[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const int r = wm * WM + 8 * i + gid, k = kk * 4 + tig;
-        a[i] = A_KMAJOR ? a_s[r * LA::PITCH + k] : a_s[k * LA::PITCH + r];
-      }
-#pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        const int c = wn * WN + 8 * j + gid, k = kk * 4 + tig;
-        b[j] = B_KMAJOR ? b_s[c * LB::PITCH + k] : b_s[k * LB::PITCH + c];
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    const int slot = kt % STAGES;
+    load_frags(fa[1], fb[1], slot, 1);
+    mma_step(fa[0], fb[0]);
+    load_frags(fa[0], fb[0], slot, 2);
+    mma_step(fa[1], fb[1]);
+    load_frags(fa[1], fb[1], slot, 3);
+    mma_step(fa[0], fb[0]);
+    if (kt + 1 < ktiles) {
+      cp_async_wait<STAGES - 2>();  // tile kt+1 has landed (kt+2, kt+3 may still be in flight)
+      __syncthreads();              // ... for every thread; nobody reads ring slot `slot` any more
+      load_frags(fa[0], fb[0], (kt + 1) % STAGES, 0);
+      mma_step(fa[1], fb[1]);
+      issue_tile(kt + STAGES);      // refill the slot that was just drained
+    } else {
+      mma_step(fa[1], fb[1]);
     }
   }
   cp_async_wait<0>();
@@ -240,19 +258,33 @@ static int launch_layout(const GemmParams& p, int a_kmajor, int b_kmajor, int ba
 }  // namespace fcest
 
 namespace fcest {
-// Tile/split heuristic: large tiles when they fill the machine, else small tiles; split K when the
-// tile count leaves SMs idle or the last wave mostly empty.
-static int choose_splitk(int M, int N, int K, int batch) {
+// Tile / split heuristic.
+//  * "big" problems (>= one wave of 128x128 tiles) use a 12-warp CTA with a 120x128 or 128x128 tile,
+//    whichever pads the M dimension less (N = 1200 time points is 10 x 120 exactly);
+//  * small problems use 64x64 tiles;
+//  * K is split only when the tile count leaves SMs idle (< 4 waves), because every split costs
+//    2 * M * N * 8 bytes of partial-tile traffic plus a reduce launch.
+struct GemmPlan { int cfg; int splitk; };  // cfg 0: 64x64, 1: 128x128, 2: 120x128
+
+static GemmPlan plan_gemm(int M, int N, int K, int batch) {
   const int sms = 148;
+  GemmPlan pl;
   const bool big = ((long long)((M + 127) / 128) * ((N + 127) / 128) * batch >= sms);
-  const int bm = big ? 128 : 64;
-  const long long tiles = (long long)((M + bm - 1) / bm) * ((N + bm - 1) / bm);
+  int bm = 64;
+  pl.cfg = 0;
+  if (big) {
+    const long long pad128 = (long long)((M + 127) / 128) * 128, pad120 = (long long)((M + 119) / 120) * 120;
+    pl.cfg = pad120 < pad128 ? 2 : 1;
+    bm = pl.cfg == 2 ? 120 : 128;
+  }
+  const int bn = big ? 128 : 64;
+  const long long tiles = (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn);
   int splitk = 1;
   if (batch == 1) {
     const int ktiles = (K + BK - 1) / BK;
     if (tiles < sms) {
       splitk = (int)((2 * sms + tiles - 1) / tiles);
-    } else {
+    } else if (tiles < 4 * sms) {
       double best = 0;
       for (int s = 1; s <= 16; ++s) {
         const double waves = (double)tiles * s / sms;
@@ -263,12 +295,13 @@ static int choose_splitk(int M, int N, int K, int batch) {
     if (splitk > ktiles / 4) splitk = ktiles / 4;
     if (splitk < 1) splitk = 1;
   }
-  return splitk;
+  pl.splitk = splitk;
+  return pl;
 }
 }  // namespace fcest
 
 extern "C" long long fcest_dgemm_workspace_bytes(int M, int N, int K, long long ldc, int batch) {
-  const int splitk = fcest::choose_splitk(M, N, K, batch);
+  const int splitk = fcest::plan_gemm(M, N, K, batch).splitk;
   return splitk > 1 ? (long long)splitk * M * ldc * 8 : 0;
 }
 
@@ -289,14 +322,15 @@ extern "C" int fcest_dgemm(int a_kmajor, int b_kmajor, int M, int N, int K, doub
   p.B = B; p.ldb = ldb; p.strideB = strideB;
   p.C = C; p.ldc = ldc; p.strideC = strideC;
   p.alpha = alpha; p.beta = beta; p.bias_row = bias_row; p.bias_col = bias_col;
-  int splitk = choose_splitk(M, N, K, batch);
+  const GemmPlan pl = plan_gemm(M, N, K, batch);
+  int splitk = pl.splitk;
   if (splitk > 1 && (workspace == nullptr || workspace_bytes < (long long)splitk * M * ldc * 8))
     splitk = 1;  // no workspace supplied: run unsplit (still correct, just fewer CTAs)
   p.splitk = splitk;
   const int ktiles = (K + BK - 1) / BK;
   p.k_per_split = ((ktiles + splitk - 1) / splitk) * BK;
   p.ws = workspace;
-  const bool big = ((long long)((M + 127) / 128) * ((N + 127) / 128) * batch >= 148);
-  if (big) return launch_layout<128, 128, 64, 32>(p, a_kmajor, b_kmajor, batch, stream);
+  if (pl.cfg == 2) return launch_layout<120, 128, 40, 32>(p, a_kmajor, b_kmajor, batch, stream);
+  if (pl.cfg == 1) return launch_layout<128, 128, 32, 32>(p, a_kmajor, b_kmajor, batch, stream);
   return launch_layout<64, 64, 32, 32>(p, a_kmajor, b_kmajor, batch, stream);
 }

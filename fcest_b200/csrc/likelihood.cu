@@ -219,22 +219,26 @@ wishart_loglik_kernel(const LikParams p) {
   }
 }
 
-// out[c] = sum_{row} X[row, c]  (fixed order -> deterministic);  optional second-level fold of
-// `fold` consecutive... (vector-A mode folds the D row-blocks of length nu onto nu outputs).
+// out[c] = sum_{row} X[row, c] in a fixed (deterministic) order; block = (32 columns) x (32 row lanes).
+// fold_len > 0 (vector-A mode) folds the cols/fold_len column groups onto fold_len outputs.
 __global__ void colsum_kernel(const double* __restrict__ X, long long ld, int rows, int cols,
-                              double* __restrict__ out, int fold_rows, int fold_len) {
-  // out index space: fold_rows == 0 -> cols outputs; else fold_len outputs, summing cols/fold_len groups
-  const int nout = fold_rows ? fold_len : cols;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nout) return;
+                              double* __restrict__ out, int fold_len) {
+  __shared__ double part[32][33];
+  const int nout = fold_len ? fold_len : cols;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int groups = fold_len ? cols / fold_len : 1;
   double s = 0.0;
-  if (!fold_rows) {
-    for (int r = 0; r < rows; ++r) s += X[(long long)r * ld + c];
-  } else {
-    for (int g = 0; g < cols / fold_len; ++g)
-      for (int r = 0; r < rows; ++r) s += X[(long long)r * ld + g * fold_len + c];
+  if (c < nout)
+    for (int g = 0; g < groups; ++g)
+      for (int r = threadIdx.y; r < rows; r += 32) s += X[(long long)r * ld + g * nout + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < nout) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += part[k][threadIdx.x];
+    out[c] = t;
   }
-  out[c] = s;
 }
 
 }  // namespace fcest
@@ -269,13 +273,14 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   FCEST_CHECK_LAUNCH();
   if (p.need_grad) {
     const int R = D * nu;
+    const dim3 cb(32, 32);
     if (a_mode == 0) {
-      colsum_kernel<<<(R + 127) / 128, 128, 0, stream>>>(ws_gA_part, R, N, R, gA, 0, 0);
+      colsum_kernel<<<(R + 31) / 32, cb, 0, stream>>>(ws_gA_part, R, N, R, gA, 0);
     } else {
-      colsum_kernel<<<(nu + 127) / 128, 128, 0, stream>>>(ws_gA_part, R, N, R, gA, 1, nu);
+      colsum_kernel<<<(nu + 31) / 32, cb, 0, stream>>>(ws_gA_part, R, N, R, gA, nu);
     }
     FCEST_CHECK_LAUNCH();
-    colsum_kernel<<<(D + 127) / 128, 128, 0, stream>>>(ws_glam_part, D, N, D, glam, 0, 0);
+    colsum_kernel<<<(D + 31) / 32, cb, 0, stream>>>(ws_glam_part, D, N, D, glam, 0);
     FCEST_CHECK_LAUNCH();
   }
   return 0;

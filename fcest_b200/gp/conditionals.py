@@ -28,6 +28,18 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(dev) -> torch.cuda.Stream:
+    """One auxiliary stream per device: the latency-bound single-matrix chain (kernel matrix ->
+    Cholesky -> inverse -> P) runs on it underneath the throughput kernels of the main stream."""
+    key = str(dev)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
 @dataclass
 class CondState:
     """Everything the backward pass needs from the forward pass."""
@@ -59,30 +71,33 @@ def conditional_forward(kernel, Z, X, q_mu, q_sqrt, vgp: bool, want_kl: bool = T
     kvar, kls = kernel.constrained()
     info = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    Lm = ops.pitched(M, M, dev)
-    ops.matern52(Z, Z, kvar, kls, Lm, JITTER)
-    ops.chol_single(Lm, info)
-    Li = ops.pitched(M, M, dev)
-    ops.tri_inv_single(Lm, Li)
-
-    P = ops.pitched(M, N, dev)
-    if vgp:
-        ops.transpose(Lm, P)
-    else:
-        Kmn = ops.pitched(M, N, dev)
-        ops.matern52(Z, X, kvar, kls, Kmn, 0.0)
-        ops.dgemm(True, False, M, N, M, Li, Kmn, P)
-
     K = M * (M + 1) // 2
     ldk = _round_up(K, 16)
-    Pk = torch.empty((N, ldk), dtype=F64, device=dev)
-    bias = torch.empty(N, dtype=F64, device=dev)
-    ops.call("fcest_pack_outer", ops.ptr(P), ops.ld(P), M, N, ops.ptr(Pk), ldk, ops.ptr(bias),
-             ops.ptr(kvar), 0 if vgp else 1)
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        # single-matrix chain (one-CTA Cholesky is latency bound) -- overlapped with tri_syrk_pack below
+        Lm = ops.pitched(M, M, dev)
+        ops.matern52(Z, Z, kvar, kls, Lm, JITTER)
+        Li = ops.pitched(M, M, dev)
+        ops.chol_inv_single(Lm, Li, info)
+        P = ops.pitched(M, N, dev)
+        if vgp:
+            ops.transpose(Lm, P)
+        else:
+            Kmn = ops.pitched(M, N, dev)
+            ops.matern52(Z, X, kvar, kls, Kmn, 0.0)
+            ops.dgemm(True, False, M, N, M, Li, Kmn, P)
+        Pk = torch.empty((N, ldk), dtype=F64, device=dev)
+        bias = torch.empty(N, dtype=F64, device=dev)
+        ops.call("fcest_pack_outer", ops.ptr(P), ops.ld(P), M, N, ops.ptr(Pk), ldk, ops.ptr(bias),
+                 ops.ptr(kvar), 0 if vgp else 1)
     Sk = torch.empty((R, ldk), dtype=F64, device=dev)
     klp = torch.empty((R, 2), dtype=F64, device=dev)
     q_sqrt = q_sqrt.contiguous()
     ops.call("fcest_tri_syrk_pack", ops.ptr(q_sqrt), R, M, ops.ptr(Sk), ldk, ops.ptr(klp))
+    main.wait_stream(side)
 
     fvar = ops.pitched(N, R, dev)
     ops.dgemm(True, True, N, R, K, Pk, Sk, fvar, bias_row=bias)

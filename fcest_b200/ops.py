@@ -42,7 +42,7 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (str(device),)
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)  # one scratch buffer per stream
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() * 8 < nbytes:
         buf = torch.empty((max(nbytes, 1 << 20) + 7) // 8, dtype=F64, device=device)
@@ -82,6 +82,11 @@ def tri_inv_single(L, Li):
     call("fcest_tri_inv_single", ptr(L), L.shape[0], ld(L), ptr(Li), ld(Li))
 
 
+def chol_inv_single(A, Li, info):
+    """A -> chol(A) (lower, in place), Li = chol(A)^-1 (blocked single-CTA kernel)."""
+    call("fcest_chol_inv_single", ptr(A), A.shape[0], ld(A), ptr(Li), ld(Li), ptr(info))
+
+
 def tril_(X, mode=0):
     call("fcest_tril", ptr(X), X.shape[0], ld(X), mode)
     return X
@@ -104,7 +109,8 @@ def sum_into(x, n, stride, scale, out, accumulate):
 
 
 def sumsq_into(x, scale, out, accumulate):
-    call("fcest_sumsq", ptr(x), x.shape[0], x.shape[1], ld(x), float(scale), ptr(out), int(accumulate))
+    ws = torch.empty(296, dtype=F64, device=x.device)
+    call("fcest_sumsq", ptr(x), x.shape[0], x.shape[1], ld(x), float(scale), ptr(out), int(accumulate), ptr(ws))
 
 
 def softplus_fwd(u, out):

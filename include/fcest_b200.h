@@ -85,6 +85,9 @@ int fcest_matern52_bwd(const double* X1, int n1, const double* X2, int n2, int d
 int fcest_chol_single(double* A, int M, long long lda, int* info, cudaStream_t stream);
 int fcest_tri_inv_single(const double* L, int M, long long ldl, double* Li, long long ldi,
                          cudaStream_t stream);
+/*      fused, blocked variant used by the conditional: A -> chol(A) in place (lower), Li = chol(A)^-1. */
+int fcest_chol_inv_single(double* A, int M, long long lda, double* Li, long long ldi, int* info,
+                          cudaStream_t stream);
 
 /* ---- glue: masks, transposes, axpby, deterministic reductions, softplus transforms. */
 int fcest_tril(double* X, int M, long long ld, int mode, cudaStream_t stream);
@@ -94,7 +97,7 @@ int fcest_axpby(long long n, double a, const double* x, double b, double* y, cud
 int fcest_sum(const double* x, long long n, long long stride, double scale, double* out,
               int accumulate, cudaStream_t stream);
 int fcest_sumsq(const double* x, int rows, int cols, long long ld, double scale, double* out,
-                int accumulate, cudaStream_t stream);
+                int accumulate, double* ws_296, cudaStream_t stream);
 int fcest_softplus_fwd(const double* u, double* out, int n, cudaStream_t stream);
 int fcest_softplus_bwd(const double* u, const double* g_c, double* g_u, int n, cudaStream_t stream);
 
