@@ -9,8 +9,11 @@
 //   mu_bar = sum_s Fbar,  v_bar = sum_s Fbar o eps / (2 sqrt v).
 //
 // Mapping: one CTA per time step n (all S samples, so the sums over s stay on chip), everything for
-// one D x D problem lives in shared memory, the three matmul-shaped pieces (G G^T, Li G, Li^T H) run
-// on the fp64 tensor pipe (DMMA.8x8x4) from conflict-free padded tiles (pitch = 4 mod 8 doubles).
+// one D x D problem lives in shared memory (~68 KB at D = 50 -> 3 CTAs per SM).  All O(D^3) work runs
+// on the fp64 tensor pipe (DMMA.8x8x4) from conflict-free padded tiles (pitch = 4 mod 8 doubles):
+// G G^T, a blocked (8x8) right-looking Cholesky whose diagonal tiles are factored + inverted in
+// registers by one warp (shuffles), the block-column recurrences for L^-1 and L^-1 y (one warp per
+// column block, warp-level sync only), and Sigma^-1 G = Li^T (Li G) done in place per column block.
 // Per-CTA partial sums for Abar / lam_bar go to a workspace and are reduced in fixed order
 // (deterministic) by colsum_kernel.
 #include <math.h>
@@ -40,56 +43,113 @@ struct LikParams {
   int need_grad;
 };
 
-__global__ void __launch_bounds__(256)
+
+// I_bb[r][k]: inverse of the b-th 8x8 diagonal Cholesky block.  Its strict lower part is stored
+// transposed in the strict upper part of diagonal tile (b,b) of T, its diagonal in dinv.
+__device__ __forceinline__ double invdiag(const double* T, const double* dinv, int Pd, int b, int r, int k) {
+  return k < r ? T[(8 * b + k) * Pd + 8 * b + r] : (k == r ? dinv[8 * b + r] : 0.0);
+}
+
+// Cholesky + inverse of one 8x8 diagonal tile, rows held in lanes 0..7 of the calling warp
+// (registers + shuffles; no shared-memory round trips inside the 8-step dependency chain).
+__device__ __forceinline__ int factor_diag_tile(double* T, double* dinv, int Pd, int b, int lane, int bad) {
+  double row[8], x[8], my_rinv = 0.0;
+  const int i = lane & 7;
+  double* base = T + (8 * b + i) * Pd + 8 * b;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { row[c] = (c <= i) ? base[c] : 0.0; x[c] = (c == i) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double piv = __shfl_sync(0xffffffffu, row[j], j);
+    if (!(piv > 0.0) && bad == 0) bad = 8 * b + j + 1;
+    const double rinv = rsqrt(piv);
+    if (i == j) my_rinv = rinv;
+    row[j] = (i == j) ? piv * rinv : row[j] * rinv;
+#pragma unroll
+    for (int k = j + 1; k < 8; ++k) {
+      const double lkj = __shfl_sync(0xffffffffu, row[j], k);
+      if (i >= k) row[k] -= row[j] * lkj;
+    }
+  }
+  // X = L^-1 by forward substitution, row i in lane i: finalise row k, broadcast it, eliminate below
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (i == k) {
+#pragma unroll
+      for (int c = 0; c <= k; ++c) x[c] *= my_rinv;
+    }
+#pragma unroll
+    for (int c = 0; c <= k; ++c) {
+      const double xk = __shfl_sync(0xffffffffu, x[c], k);
+      if (i > k) x[c] -= row[k] * xk;
+    }
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c <= i) base[c] = row[c];                                   // L (lower, incl. diagonal)
+      if (c < i) T[(8 * b + c) * Pd + 8 * b + i] = x[c];              // I^T (strict upper)
+    }
+    dinv[8 * b + i] = my_rinv;
+  }
+  return bad;
+}
+
+// One CTA (8 warps) per time step; per MC sample a blocked (8x8 tiles) Cholesky / inverse on the fp64
+// tensor pipe.  Shared memory: G (D x nu, later H = Li G, then Q = Sigma^-1 G, in place per column
+// block), T (lower: Sigma -> L; strict upper: Li^T), a y column block and per-warp scratch tiles.
+__global__ void __launch_bounds__(256, 3)
 wishart_loglik_kernel(const LikParams p) {
   extern __shared__ __align__(16) double sm[];
   const int D = p.D, nu = p.nu, R = D * nu;
   const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
   const int Pd = pitch4(Dp), Pg = pitch4(Np);
-  double* G = sm;                 // Dp x Pg   (later holds Q = Sigma^-1 G)
-  double* H = G + Dp * Pg;        // Dp x Pg
-  double* Sg = H + Dp * Pg;       // Dp x Pd   Sigma -> L (lower)
-  double* Li = Sg + Dp * Pd;      // Dp x Pd   L^-1 (lower, upper zero)
-  double* yv = Li + Dp * Pd;      // Dp
-  double* zv = yv + Dp;           // Dp
-  double* al = zv + Dp;           // Dp  alpha
-  double* ds = al + Dp;           // Dp  diag(Sigma^-1)
-  double* spl = ds + Dp;          // Dp  softplus(lam)
-  double* cv = spl + Dp;          // Np  c = alpha^T G
-  double* red = cv + Np;          // 32
+  const int nbD = Dp / 8, nbN = Np / 8;
+  double* G = sm;                 // Dp x Pg
+  double* T = G + Dp * Pg;        // Dp x Pd
+  double* Yb = T + Dp * Pd;       // Dp x 12 : column 0 = y -> z -> alpha
+  double* scr = Yb + Dp * 12;     // 8 warps x 96
+  double* dinv = scr + 8 * 96;    // Dp  1 / L_dd
+  double* yv = dinv + Dp;         // Dp
+  double* spl = yv + Dp;          // Dp  softplus(lam)
+  double* ds = spl + Dp;          // Dp  diag(Sigma^-1)
+  double* cv = ds + Dp;           // Np  c = alpha^T G = y^T Q
+  double* scal = cv + Np;         // [0] = |z|^2
+  __shared__ int bad_s;
 
   const int n = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = 8;
   const int gid = lane >> 2, tig = lane & 3;
-  const int nbD = Dp / 8, nbN = Np / 8;
   const double w = 1.0 / p.S;
   const double* fm = p.fmean + (long long)n * p.ldf;
   const double* fv = p.fvar + (long long)n * p.ldf;
+  double* myscr = scr + warp * 96;
 
   for (int d = tid; d < Dp; d += blockDim.x) {
     yv[d] = d < D ? p.y[(long long)n * D + d] : 0.0;
     spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
   }
+  if (tid == 0) bad_s = 0;
   double ve_acc = 0.0;
   int bad = 0;
 
   for (int s = 0; s < p.S; ++s) {
     const double* ep = p.eps + ((long long)s * p.N + n) * R;
     __syncthreads();
-    // 1. G = A o (mu + sqrt(v) eps), zero padding; Li = 0
+    // P1. G = A o (mu + sqrt(v) eps) with zero padding; y block
     for (int e = tid; e < Dp * Pg; e += blockDim.x) {
       const int d = e / Pg, k = e - d * Pg;
       double v = 0.0;
       if (d < D && k < nu) {
         const int r = d * nu + k;
-        const double f = fm[r] + sqrt(fv[r]) * ep[r];
-        v = (p.a_mode == 0 ? p.A[r] : p.A[k]) * f;
+        v = (p.a_mode == 0 ? p.A[r] : p.A[k]) * (fm[r] + sqrt(fv[r]) * ep[r]);
       }
       G[e] = v;
     }
-    for (int e = tid; e < Dp * Pd; e += blockDim.x) Li[e] = 0.0;
+    for (int e = tid; e < Dp * 12; e += blockDim.x) Yb[e] = (e % 12 == 0) ? yv[e / 12] : 0.0;
     __syncthreads();
-    // 2. Sigma (lower tiles) = G G^T + diag(softplus(lam)); padded diagonal = 1
+    // P2. Sigma (lower tiles) = G G^T + diag(softplus(lam)); padded diagonal = 1
     for (int t = warp; t < nbD * (nbD + 1) / 2; t += nwarps) {
       int ib = 0, rem = t;
       while (rem > ib) { rem -= ib + 1; ++ib; }
@@ -101,96 +161,191 @@ wishart_loglik_kernel(const LikParams p) {
       const int row = 8 * ib + gid, col = 8 * jb + 2 * tig;
       if (row == col) c0 += spl[row];
       if (row == col + 1) c1 += spl[row];
-      Sg[row * Pd + col] = c0;
-      Sg[row * Pd + col + 1] = c1;
+      T[row * Pd + col] = c0;
+      T[row * Pd + col + 1] = c1;
     }
     __syncthreads();
-    // 3. in-place right-looking Cholesky of the leading D x D block (lower)
-    for (int j = 0; j < D; ++j) {
-      const double piv = Sg[j * Pd + j];
-      if (!(piv > 0.0)) { if (!bad) bad = j + 1; break; }  // uniform: every thread reads the same piv
-      const double dj = sqrt(piv), inv = 1.0 / dj;
-      for (int i = j + 1 + tid; i < D; i += blockDim.x) Sg[i * Pd + j] *= inv;
+    // P3. blocked right-looking Cholesky; diagonal tiles are factored and inverted by warp 0
+    if (warp == 0) bad = factor_diag_tile(T, dinv, Pd, 0, lane, bad);
+    __syncthreads();
+    for (int jb = 0; jb < nbD; ++jb) {
+      // panel: L[ib,jb] = S[ib,jb] I_jj^T
+      for (int ib = jb + 1 + warp; ib < nbD; ib += nwarps) {
+        double* tile = T + (8 * ib + gid) * Pd + 8 * jb;
+        double c0 = 0.0, c1 = 0.0;
+        const double a0 = tile[tig], a1 = tile[4 + tig];
+        dmma(c0, c1, a0, invdiag(T, dinv, Pd, jb, gid, tig));
+        dmma(c0, c1, a1, invdiag(T, dinv, Pd, jb, gid, 4 + tig));
+        __syncwarp();
+        tile[2 * tig] = c0;
+        tile[2 * tig + 1] = c1;
+      }
       __syncthreads();
-      if (tid == 0) Sg[j * Pd + j] = dj;
-      for (int i = j + 1 + warp; i < D; i += nwarps) {
-        const double lij = Sg[i * Pd + j];
-        for (int k = j + 1 + lane; k <= i; k += 32) Sg[i * Pd + k] -= lij * Sg[k * Pd + j];
+      // trailing update S[ib,kb] -= L[ib,jb] L[kb,jb]^T (jb < kb <= ib); warp 0 owns the next
+      // diagonal tile and factors it straight away (critical path), warps 1..7 share the rest
+      const int m = nbD - 1 - jb;
+      if (m > 0) {
+        if (warp == 0) {
+          const int ib = jb + 1;
+          double* ct = T + (8 * ib + gid) * Pd + 8 * ib + 2 * tig;
+          double c0 = ct[0], c1 = ct[1];
+          const double* la = T + (8 * ib + gid) * Pd + 8 * jb;
+          dmma(c0, c1, -la[tig], la[tig]);
+          dmma(c0, c1, -la[4 + tig], la[4 + tig]);
+          ct[0] = c0;
+          ct[1] = c1;
+          __syncwarp();
+          bad = factor_diag_tile(T, dinv, Pd, ib, lane, bad);
+        } else {
+          for (int t = warp; t < m * (m + 1) / 2; t += nwarps - 1) {  // t = 0 is warp 0's tile
+            int ii = 0, rem = t;
+            while (rem > ii) { rem -= ii + 1; ++ii; }
+            const int ib = jb + 1 + ii, kb = jb + 1 + rem;
+            double* ct = T + (8 * ib + gid) * Pd + 8 * kb + 2 * tig;
+            double c0 = ct[0], c1 = ct[1];
+            const double* la = T + (8 * ib + gid) * Pd + 8 * jb;
+            const double* lb = T + (8 * kb + gid) * Pd + 8 * jb;
+            dmma(c0, c1, -la[tig], lb[tig]);
+            dmma(c0, c1, -la[4 + tig], lb[4 + tig]);
+            ct[0] = c0;
+            ct[1] = c1;
+          }
+        }
       }
       __syncthreads();
     }
-    if (bad) break;
-    // 4. forward substitution with RHS [I | y]: column c < D -> Li[:, c], column D -> z
-    if (tid <= D) {
-      const int c = tid;
-      if (c < D) {
-        for (int i = c; i < D; ++i) {
-          double sacc = (i == c) ? 1.0 : 0.0;
-          const double* Lrow = Sg + i * Pd;
-          for (int k = c; k < i; ++k) sacc -= Lrow[k] * Li[k * Pd + c];
-          Li[i * Pd + c] = sacc / Lrow[i];
+    // P4. columns of Li = L^-1 (one warp per column block, no block barriers) and z = L^-1 y
+    for (int task = warp; task <= nbD; task += nwarps) {
+      if (task < nbD) {
+        if (!p.need_grad) continue;
+        const int jb = task;
+        for (int ib = jb + 1; ib < nbD; ++ib) {
+          double c0 = 0.0, c1 = 0.0;
+          for (int kb = jb; kb < ib; ++kb) {
+            const double* la = T + (8 * ib + gid) * Pd + 8 * kb;
+            double b0, b1;
+            if (kb == jb) {
+              b0 = invdiag(T, dinv, Pd, jb, tig, gid);
+              b1 = invdiag(T, dinv, Pd, jb, 4 + tig, gid);
+            } else {
+              const double* xb = T + (8 * jb + gid) * Pd + 8 * kb;
+              b0 = xb[tig];
+              b1 = xb[4 + tig];
+            }
+            dmma(c0, c1, la[tig], b0);
+            dmma(c0, c1, la[4 + tig], b1);
+          }
+          myscr[gid * 12 + 2 * tig] = c0;
+          myscr[gid * 12 + 2 * tig + 1] = c1;
+          __syncwarp();
+          double x0 = 0.0, x1 = 0.0;
+          dmma(x0, x1, invdiag(T, dinv, Pd, ib, gid, tig), myscr[tig * 12 + gid]);
+          dmma(x0, x1, invdiag(T, dinv, Pd, ib, gid, 4 + tig), myscr[(4 + tig) * 12 + gid]);
+          T[(8 * jb + 2 * tig) * Pd + 8 * ib + gid] = -x0;      // Li[ib,jb]^T into the upper tile (jb,ib)
+          T[(8 * jb + 2 * tig + 1) * Pd + 8 * ib + gid] = -x1;
+          __syncwarp();
         }
       } else {
-        for (int i = 0; i < D; ++i) {
-          double sacc = yv[i];
-          const double* Lrow = Sg + i * Pd;
-          for (int k = 0; k < i; ++k) sacc -= Lrow[k] * zv[k];
-          zv[i] = sacc / Lrow[i];
+        for (int ib = 0; ib < nbD; ++ib) {
+          double* yt = Yb + (8 * ib + gid) * 12 + 2 * tig;
+          double c0 = yt[0], c1 = yt[1];
+          for (int kb = 0; kb < ib; ++kb) {
+            const double* la = T + (8 * ib + gid) * Pd + 8 * kb;
+            dmma(c0, c1, -la[tig], Yb[(8 * kb + tig) * 12 + gid]);
+            dmma(c0, c1, -la[4 + tig], Yb[(8 * kb + 4 + tig) * 12 + gid]);
+          }
+          myscr[gid * 12 + 2 * tig] = c0;
+          myscr[gid * 12 + 2 * tig + 1] = c1;
+          __syncwarp();
+          double x0 = 0.0, x1 = 0.0;
+          dmma(x0, x1, invdiag(T, dinv, Pd, ib, gid, tig), myscr[tig * 12 + gid]);
+          dmma(x0, x1, invdiag(T, dinv, Pd, ib, gid, 4 + tig), myscr[(4 + tig) * 12 + gid]);
+          yt[0] = x0;
+          yt[1] = x1;
+          __syncwarp();
         }
+        double q = 0.0;
+        for (int d = lane; d < D; d += 32) q += Yb[d * 12] * Yb[d * 12];
+        q = warp_sum(q);
+        if (lane == 0) scal[0] = q;
       }
     }
     __syncthreads();
-    // 5. log-density; alpha = Li^T z, diag(Sigma^-1)
     if (warp == 0) {
-      double ld = 0.0, q = 0.0;
-      for (int d = lane; d < D; d += 32) { ld += log(Sg[d * Pd + d]); q += zv[d] * zv[d]; }
+      double ld = 0.0;
+      for (int d = lane; d < D; d += 32) ld -= log(dinv[d]);
       ld = warp_sum(ld);
-      q = warp_sum(q);
-      ve_acc += w * (-0.5 * D * 1.8378770664093453 - ld - 0.5 * q);
+      ve_acc += w * (-0.5 * D * 1.8378770664093453 - ld - 0.5 * scal[0]);
     }
     if (!p.need_grad) continue;
-    for (int d = tid; d < Dp; d += blockDim.x) {
-      double a = 0.0, sq = 0.0;
-      if (d < D)
-        for (int k = d; k < D; ++k) { const double l = Li[k * Pd + d]; a += l * zv[k]; sq += l * l; }
-      al[d] = a;
-      ds[d] = sq;
+    // P5. per column block (one warp each, in place): H = Li G, then Q = Li^T H = Sigma^-1 G;
+    //     the y block gives alpha = Li^T z
+    for (int task = warp; task <= nbN; task += nwarps) {
+      const bool ycol = (task == nbN);
+      double* B = ycol ? Yb : G + 8 * task;
+      const int Pb = ycol ? 12 : Pg;
+      if (!ycol) {
+        // H = Li B, bottom-up: tile ib only needs input tiles kb <= ib, so it can be overwritten at once
+        for (int ib = nbD - 1; ib >= 0; --ib) {
+          double c0 = 0.0, c1 = 0.0;
+          for (int kb = 0; kb <= ib; ++kb) {
+            double a0, a1;
+            if (kb == ib) {
+              a0 = invdiag(T, dinv, Pd, ib, gid, tig);
+              a1 = invdiag(T, dinv, Pd, ib, gid, 4 + tig);
+            } else {
+              a0 = T[(8 * kb + tig) * Pd + 8 * ib + gid];
+              a1 = T[(8 * kb + 4 + tig) * Pd + 8 * ib + gid];
+            }
+            dmma(c0, c1, a0, B[(8 * kb + tig) * Pb + gid]);
+            dmma(c0, c1, a1, B[(8 * kb + 4 + tig) * Pb + gid]);
+          }
+          __syncwarp();
+          B[(8 * ib + gid) * Pb + 2 * tig] = c0;
+          B[(8 * ib + gid) * Pb + 2 * tig + 1] = c1;
+        }
+        __syncwarp();
+      }
+      // Q = Li^T H, top-down: tile mb only needs input tiles kb >= mb
+      for (int mb = 0; mb < nbD; ++mb) {
+        double c0 = 0.0, c1 = 0.0;
+        for (int kb = mb; kb < nbD; ++kb) {
+          double a0, a1;
+          if (kb == mb) {
+            a0 = invdiag(T, dinv, Pd, mb, tig, gid);
+            a1 = invdiag(T, dinv, Pd, mb, 4 + tig, gid);
+          } else {
+            a0 = T[(8 * mb + gid) * Pd + 8 * kb + tig];
+            a1 = T[(8 * mb + gid) * Pd + 8 * kb + 4 + tig];
+          }
+          dmma(c0, c1, a0, B[(8 * kb + tig) * Pb + gid]);
+          dmma(c0, c1, a1, B[(8 * kb + 4 + tig) * Pb + gid]);
+        }
+        __syncwarp();
+        B[(8 * mb + gid) * Pb + 2 * tig] = c0;
+        B[(8 * mb + gid) * Pb + 2 * tig + 1] = c1;
+      }
     }
     __syncthreads();
+    // P6. c = y^T Q (= alpha^T G), diag(Sigma^-1)_d = sum_k Li[k,d]^2
     for (int k = tid; k < Np; k += blockDim.x) {
       double c = 0.0;
       if (k < nu)
-        for (int d = 0; d < D; ++d) c += al[d] * G[d * Pg + k];
+        for (int d = 0; d < D; ++d) c += yv[d] * G[d * Pg + k];
       cv[k] = c;
     }
-    // 6. H = Li G   (lower-triangular A operand: k-loop stops at the diagonal block)
-    for (int t = warp; t < nbD * nbN; t += nwarps) {
-      const int ib = t / nbN, cb = t - ib * nbN;
-      double c0 = 0.0, c1 = 0.0;
-      const double* la = Li + (8 * ib + gid) * Pd + tig;
-      const double* gb = G + tig * Pg + 8 * cb + gid;
-      for (int k0 = 0; k0 < 8 * (ib + 1); k0 += 4) dmma(c0, c1, la[k0], gb[k0 * Pg]);
-      const int row = 8 * ib + gid, col = 8 * cb + 2 * tig;
-      H[row * Pg + col] = c0;
-      H[row * Pg + col + 1] = c1;
+    for (int d = tid; d < Dp; d += blockDim.x) {
+      double sq = dinv[d] * dinv[d];
+      const int b = d >> 3;
+      for (int k = d + 1; k < 8 * (b + 1); ++k) { const double l = T[d * Pd + k]; sq += l * l; }
+      for (int k = 8 * (b + 1); k < D; ++k) { const double l = T[d * Pd + k]; sq += l * l; }
+      ds[d] = sq;
     }
     __syncthreads();
-    // 7. Q = Li^T H = Sigma^-1 G  (written over G)
-    for (int t = warp; t < nbD * nbN; t += nwarps) {
-      const int mb = t / nbN, cb = t - mb * nbN;
-      double c0 = 0.0, c1 = 0.0;
-      const double* la = Li + tig * Pd + 8 * mb + gid;
-      const double* hb = H + tig * Pg + 8 * cb + gid;
-      for (int k0 = 8 * mb; k0 < Dp; k0 += 4) dmma(c0, c1, la[k0 * Pd], hb[k0 * Pg]);
-      const int row = 8 * mb + gid, col = 8 * cb + 2 * tig;
-      G[row * Pg + col] = c0;
-      G[row * Pg + col + 1] = c1;
-    }
-    __syncthreads();
-    // 8. gradients
+    // P7. gradients
     for (int r = tid; r < R; r += blockDim.x) {
       const int d = r / nu, k = r - d * nu;
-      const double gbar = w * (-G[d * Pg + k] + al[d] * cv[k]);
+      const double gbar = w * (-G[d * Pg + k] + Yb[d * 12] * cv[k]);
       const double a = (p.a_mode == 0 ? p.A[r] : p.A[k]);
       const double sd = sqrt(fv[r]), e = ep[r];
       const double f = fm[r] + sd * e;
@@ -208,14 +363,17 @@ wishart_loglik_kernel(const LikParams p) {
       }
     }
     for (int d = tid; d < D; d += blockDim.x) {
-      const double v = sigmoid_d(p.lam[d]) * w * (-0.5 * ds[d] + 0.5 * al[d] * al[d]);
+      const double al = Yb[d * 12];
+      const double v = sigmoid_d(p.lam[d]) * w * (-0.5 * ds[d] + 0.5 * al * al);
       const long long o = (long long)n * D + d;
       if (s == 0) p.glam_part[o] = v; else p.glam_part[o] += v;
     }
   }
+  if (warp == 0 && lane == 0 && bad) atomicMax(&bad_s, bad);
+  __syncthreads();
   if (tid == 0) {
-    p.ve[n] = bad ? nan("") : ve_acc;
-    p.info[n] = bad;
+    p.ve[n] = bad_s ? nan("") : ve_acc;
+    p.info[n] = bad_s;
   }
 }
 
@@ -248,7 +406,7 @@ using namespace fcest;
 extern "C" long long fcest_wishart_loglik_smem_bytes(int D, int nu) {
   const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
   const int Pd = pitch4(Dp), Pg = pitch4(Np);
-  return (long long)sizeof(double) * (2LL * Dp * Pg + 2LL * Dp * Pd + 5 * Dp + Np + 32);
+  return (long long)sizeof(double) * ((long long)Dp * Pg + (long long)Dp * Pd + 12LL * Dp + 8 * 96 + 4 * Dp + Np + 8);
 }
 
 extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, long long ldf,
