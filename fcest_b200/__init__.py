@@ -3,9 +3,9 @@
 Importing the package does not need a GPU; calling any operator does (there is no CPU fallback).
 """
 from . import helpers, models
-from .models import (SparseVariationalWishartProcess, VariationalWishartProcess,
+from .models import (SlidingWindows, SparseVariationalWishartProcess, VariationalWishartProcess,
                      WishartProcessLikelihood)
 
 __version__ = "0.1.0"
 __all__ = ["helpers", "models", "VariationalWishartProcess", "SparseVariationalWishartProcess",
-           "WishartProcessLikelihood"]
+           "WishartProcessLikelihood", "SlidingWindows"]

@@ -1,0 +1,156 @@
+"""``fcest.models.sliding_windows`` mirror: sliding-window TVFC estimation on B200.
+
+Same class, constructor and method names / defaults as the reference
+(``fcest/models/sliding_windows.py:27-427``).  ``overlapping_windowed_cov_estimation`` and the
+cross-validated window search run in ``fcest_window_cov`` / ``fcest_window_cv``; inputs and outputs stay
+NumPy / pandas as in the reference.  Out of scope here: the optional Butterworth
+high-pass filter that the reference applies when ``repetition_time`` is passed to
+``overlapping_windowed_cov_estimation``, and CSV save / load.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import ops
+
+# scipy.stats._multivariate._eigvalsh_to_eps: 1e6 * eps relative eigenvalue threshold for "singular"
+_SINGULAR_REL_TOL = 1e6 * float(np.finfo(np.float64).eps)
+
+
+class SlidingWindows:
+    """Main class for sliding-windows methods for time-varying functional connectivity (TVFC) estimation."""
+
+    def __init__(
+            self,
+            x_train_locations: np.array,
+            y_train_locations: np.array,
+            repetition_time: float = None,
+            window_shape: str = 'rectangle',
+            device="cuda",
+    ) -> None:
+        self.x_train = x_train_locations
+        self.y_train = y_train_locations
+        assert len(x_train_locations) == len(y_train_locations)
+        self.num_time_steps = y_train_locations.shape[0]  # N
+        self.num_time_series = y_train_locations.shape[1]  # D
+        self.device = device
+        if repetition_time is None:
+            logging.info("No repetition time found, assuming we are running simulations.")
+            repetition_time = 1.0
+        self.repetition_time = repetition_time
+        self._set_min_max_proposed_window_length()
+        if window_shape == 'tapered':
+            logging.error("Tapered sliding windows not implemented yet.")
+        elif window_shape != 'rectangle':
+            logging.error("Other window types not implemented yet.")
+
+    def _y_device(self) -> torch.Tensor:
+        return torch.tensor(np.ascontiguousarray(self.y_train, dtype=np.float64), device=self.device)
+
+    def estimate_static_functional_connectivity(self, connectivity_metric: str, return_structure: bool = True):
+        """sliding_windows.py:74-107 (plain NumPy, not on the hot path)."""
+        match connectivity_metric:
+            case 'covariance':
+                sfc_estimate = np.cov(self.y_train.T)
+            case 'correlation':
+                sfc_estimate = np.corrcoef(self.y_train.T)
+            case _:
+                raise NotImplementedError(f"Connectivity metric {connectivity_metric:s} not recognized.")
+        if return_structure:
+            sfc_estimate = np.tile(sfc_estimate, reps=(self.num_time_steps, 1, 1))
+        return sfc_estimate
+
+    def overlapping_windowed_cov_estimation(
+            self,
+            window_length: int,
+            step_size: int = 1,
+            repetition_time: float = None,
+            connectivity_metric: str = 'covariance',
+    ) -> np.array:
+        """Overlapping sliding-windows estimate, (N, D, D) -- sliding_windows.py:109-174."""
+        if repetition_time is not None:
+            raise NotImplementedError(
+                "High-pass filtering before windowing (reference filtering.py:12-93) is outside the B200 hot "
+                "path; filter the data first and call with repetition_time=None.")
+        n, d = self.num_time_steps, self.num_time_series
+        y = self._y_device()
+        out = torch.empty((n, d, d), dtype=torch.float64, device=y.device)
+        ops.call("fcest_window_cov", ops.ptr(y), n, d, int(window_length), int(step_size),
+                 1 if connectivity_metric == 'correlation' else 0, ops.ptr(out))
+        return out.cpu().numpy()
+
+    def compute_cross_validated_optimal_window_length(
+            self,
+            window_length_step_size: int = 2,
+            eval_location_step_size: int = 1,
+    ) -> int:
+        results_df = self.find_cross_validated_optimal_window_length(
+            window_length_step_size=window_length_step_size,
+            eval_location_step_size=eval_location_step_size
+        )
+        return self.get_optimal_window_length(results_df)
+
+    def find_cross_validated_optimal_window_length(
+            self,
+            window_length_step_size: int = 2,
+            eval_location_step_size: int = 1,
+    ) -> pd.DataFrame:
+        """DataFrame (eval locations x proposed window lengths) of held-out log densities
+        (sliding_windows.py:199-274)."""
+        proposal_window_length_range = np.arange(
+            self.minimum_proposal_window_length, self.maximum_proposal_window_length, window_length_step_size)
+        num_w = len(proposal_window_length_range)
+        logging.info(f"Proposing {num_w:d} window lengths (from {self.minimum_proposal_window_length:d} to "
+                     f"{self.maximum_proposal_window_length:d}, in steps of {window_length_step_size:d}).")
+        t_lo = int((self.maximum_proposal_window_length - 1) / 2)
+        t_hi = self.num_time_steps - int((self.maximum_proposal_window_length + 1) / 2)
+        eval_locations = np.arange(t_lo, t_hi, eval_location_step_size)
+        num_t = len(eval_locations)
+        logging.info(f"Evaluating on {num_t:d} observations (from position {t_lo:d} to {t_hi:d}).")
+        y = self._y_device()
+        table = torch.empty((num_t, num_w), dtype=torch.float64, device=y.device)
+        if num_t > 0 and num_w > 0:
+            ops.call("fcest_window_cv", ops.ptr(y), self.num_time_steps, self.num_time_series,
+                     int(proposal_window_length_range[0]), int(window_length_step_size), num_w, int(t_lo),
+                     int(eval_location_step_size), num_t, _SINGULAR_REL_TOL, ops.ptr(table), num_w)
+        return pd.DataFrame(table.cpu().numpy(), index=eval_locations, columns=proposal_window_length_range)
+
+    def _set_min_max_proposed_window_length(
+            self,
+            min_proposal_window_length_seconds: float = 20.0,
+            max_proposal_window_length_seconds: float = 180.0,
+    ) -> None:
+        """sliding_windows.py:276-304 (repetition_time is never None here, see :63-66, so the per-N
+        table of the reference, :306-329, is unreachable)."""
+        lo = int(np.ceil(min_proposal_window_length_seconds / self.repetition_time))
+        hi = int(np.minimum(
+            int(np.ceil(self.num_time_steps * self.repetition_time / 2 / self.repetition_time)),
+            int(np.ceil(max_proposal_window_length_seconds / self.repetition_time))))
+        if lo % 2 == 0:
+            lo += 1
+        if hi % 2 == 0:
+            hi += 1
+        self.minimum_proposal_window_length = lo
+        self.maximum_proposal_window_length = hi
+
+    @staticmethod
+    def get_optimal_window_length(results_df: pd.DataFrame) -> int:
+        """sliding_windows.py:331-350."""
+        mean_results_df = results_df.mean(axis=0)
+        optimal_window_length = mean_results_df.index[mean_results_df.argmax()]
+        logging.info(f"Obtained optimal window length: {optimal_window_length:d} TRs.")
+        return optimal_window_length
+
+    def windowed_cov_estimation(self, num_windows: int) -> np.array:
+        """Segmented, non-overlapping windows (sliding_windows.py:352-372; plain NumPy)."""
+        num_time_steps, num_time_series = self.y_train.shape
+        cov_structure = np.zeros((num_time_steps, num_time_series, num_time_series))
+        window_length = num_time_steps / num_windows
+        for i_window in range(num_windows):
+            idx = np.arange(int(i_window * window_length), int((i_window + 1) * window_length))
+            cov_structure[idx, :, :] = np.cov(self.y_train[idx, :].T)
+        return cov_structure

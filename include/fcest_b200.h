@@ -125,6 +125,19 @@ int fcest_cov_moments(const double* fmean, const double* fvar, long long ldf, co
 int fcest_batched_chol_info(const double* A, int B, int D, double atol, int* info,
                             cudaStream_t stream);
 
+/* ---- sliding windows: SlidingWindows.overlapping_windowed_cov_estimation
+ *      (fcest/models/sliding_windows.py:109-174; np.cov per zero-padded window, optional cov -> corr of
+ *      fcest/helpers/array_operations.py:37-53) and find_cross_validated_optimal_window_length (:199-274).
+ *   window_cov : y (N,D) -> out (N,D,D); out[i] = cov(padded rows [i*step, i*step + w)), i < N/step, else 0.
+ *   window_cv  : table[ti*ldt + wi] = logpdf(y_t; 0, cov(window of length w around t without its centre row)),
+ *                w = w_min + wi*w_step, t = t_min + ti*t_step; -inf when the window covariance is singular
+ *                (w - 2 < D, or a Cholesky pivot below rel_tol * max diagonal). */
+int fcest_window_cov(const double* y, int N, int D, int window_length, int step_size, int corr,
+                     double* out, cudaStream_t stream);
+int fcest_window_cv(const double* y, int N, int D, int w_min, int w_step, int num_w, int t_min,
+                    int t_step, int num_t, double rel_tol, double* table, long long ldt,
+                    cudaStream_t stream);
+
 /* ---- instrumentation: number of kernels this library has launched since load (bench.py "gpu_launches"). */
 long long fcest_launch_count(void);
 long long fcest_launch_count_add(long long n);

@@ -1,0 +1,115 @@
+"""Generates the committed golden fixtures.  Run in the BUILD container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+* sliding_*.npz -- outputs of the REFERENCE's own SlidingWindows class (fcest/models/sliding_windows.py),
+  imported from the read-only mount with the unrelated third-party imports stubbed.
+* wishart_*.npz -- outputs of the CPU oracle (oracle/wishart_oracle.py).  TensorFlow / GPflow cannot be
+  installed here, so these pin the *restatement* (regression fixtures), not the reference: "parity
+  unpinned" for the Wishart path, as stated in the oracle header and DESIGN.md.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def import_reference_sliding_windows():
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _Callable:
+        def __init__(self, *a, **k):
+            pass
+
+    stub("tensorflow", Tensor=object, Variable=object)
+    stub("tensorflow.python"); stub("tensorflow.python.framework")
+    stub("tensorflow.python.framework.errors", InvalidArgumentError=Exception)
+    stub("gpflow", set_trainable=lambda *a, **k: None)
+    stub("gpflow.likelihoods", MonteCarloLikelihood=object)
+    stub("gpflow.kernels", Kernel=object, Matern52=_Callable)
+    models = stub("gpflow.models")
+    models.vgp = stub("gpflow.models.vgp", VGP=object)
+    models.svgp = stub("gpflow.models.svgp", SVGP=object)
+    stub("gpflow.monitor", ModelToTensorBoard=object, Monitor=object, MonitorTaskGroup=object,
+         ScalarToTensorBoard=object)
+    sys.modules["gpflow"].models = models
+    sys.modules["gpflow"].kernels = sys.modules["gpflow.kernels"]
+    stub("rpy2"); stub("rpy2.robjects", pandas2ri=None, r=None)
+    stub("rpy2.robjects.packages", importr=lambda *a, **k: None)
+    stub("rpy2.robjects.conversion", localconverter=None)
+    stub("statsmodels"); stub("statsmodels.tsa"); stub("statsmodels.tsa.ar_model", AutoReg=object)
+    sys.path.insert(0, "/root/reference")
+    from fcest.models.sliding_windows import SlidingWindows
+    return SlidingWindows
+
+
+def make_sliding():
+    SlidingWindows = import_reference_sliding_windows()
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [("a", 60, 4, 9, 1), ("b", 61, 3, 10, 2), ("c", 48, 7, 15, 3), ("d", 40, 5, 4, 1)]
+    for tag, n, d, w, step in cases:
+        y = rng.standard_normal((n, d)) + (3.0 if tag == "c" else 0.0)
+        x = np.linspace(0, 1, n)[:, None]
+        sw = SlidingWindows(x, y)
+        out[f"y_{tag}"] = y
+        out[f"meta_{tag}"] = np.array([w, step])
+        out[f"cov_{tag}"] = sw.overlapping_windowed_cov_estimation(w, step_size=step)
+        out[f"corr_{tag}"] = sw.overlapping_windowed_cov_estimation(w, step_size=step,
+                                                                     connectivity_metric="correlation")
+    np.savez_compressed(os.path.join(HERE, "sliding_windows.npz"), **out)
+    # cross-validated window search (reference table as a DataFrame -> arrays)
+    cv = {}
+    for tag, n, d in [("a", 70, 3), ("b", 64, 25)]:  # b: D=25 makes short windows rank deficient (-inf)
+        y = rng.standard_normal((n, d))
+        sw = SlidingWindows(np.linspace(0, 1, n)[:, None], y)
+        df = sw.find_cross_validated_optimal_window_length()
+        cv[f"y_{tag}"] = y
+        cv[f"table_{tag}"] = df.to_numpy(dtype=np.float64)
+        cv[f"locs_{tag}"] = df.index.to_numpy()
+        cv[f"windows_{tag}"] = df.columns.to_numpy()
+        cv[f"best_{tag}"] = np.array(sw.get_optimal_window_length(df))
+        cv[f"bounds_{tag}"] = np.array([sw.minimum_proposal_window_length, sw.maximum_proposal_window_length])
+    sw = SlidingWindows(np.zeros((1200, 1)), np.zeros((1200, 2)))
+    cv["bounds_1200"] = np.array([sw.minimum_proposal_window_length, sw.maximum_proposal_window_length])
+    np.savez_compressed(os.path.join(HERE, "sliding_cv.npz"), **cv)
+    print("sliding fixtures written")
+
+
+def make_wishart():
+    import torch
+    from oracle import wishart_oracle as wo
+    out = {}
+    for tag, kind, N, D, S, M in [("svgp", "svgp", 36, 4, 3, 11), ("vgp", "vgp", 25, 3, 4, None)]:
+        x, y, eps, p = wo.make_inputs(N, D, S, M=M, seed=5)
+        elbo, g = wo.elbo_and_grad(kind, p, x, y, eps)
+        out[f"{tag}_elbo"] = np.array(elbo)
+        for k, v in g.items():
+            out[f"{tag}_grad_{k}"] = v.numpy()
+        xn = torch.linspace(-0.05, 1.05, 9, dtype=torch.float64)[:, None]
+        fm, fv = wo.svgp_predict_f(xn, p) if kind == "svgp" else wo.vgp_predict_f(xn, x, p)
+        gen = torch.Generator().manual_seed(3)
+        e2 = torch.randn(16, 9, D, D, dtype=torch.float64, generator=gen)
+        cm, cs = wo.predict_cov(fm, fv, p["A"], p["lam"], e2, D)
+        rm, rs = wo.predict_corr(fm, fv, p["A"], p["lam"], e2, D)
+        out[f"{tag}_fmean"] = fm.numpy(); out[f"{tag}_fvar"] = fv.numpy()
+        out[f"{tag}_cov_mean"] = cm.numpy(); out[f"{tag}_cov_std"] = cs.numpy()
+        out[f"{tag}_corr_mean"] = rm.numpy(); out[f"{tag}_corr_std"] = rs.numpy()
+        out[f"{tag}_shape"] = np.array([N, D, S, -1 if M is None else M])
+    np.savez_compressed(os.path.join(HERE, "wishart_oracle.npz"), **out)
+    print("wishart fixtures written")
+
+
+if __name__ == "__main__":
+    make_wishart()
+    make_sliding()

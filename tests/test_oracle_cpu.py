@@ -1,0 +1,140 @@
+"""CPU tests (no GPU): the oracle against the reference's golden vectors and against itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sliding_oracle as so
+from oracle import wishart_oracle as wo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---- sliding windows: oracle vs outputs of the reference itself (tests/golden/make_golden.py) -------
+def test_sliding_oracle_matches_reference_fixtures():
+    g = np.load(os.path.join(GOLD, "sliding_windows.npz"))
+    for tag in "abcd":
+        y = g[f"y_{tag}"]
+        w, step = (int(v) for v in g[f"meta_{tag}"])
+        cov = so.overlapping_windowed_cov(y, w, step)
+        corr = so.overlapping_windowed_cov(y, w, step, "correlation")
+        assert cov.shape == g[f"cov_{tag}"].shape
+        scale = max(1.0, np.abs(g[f"cov_{tag}"]).max())
+        assert np.abs(cov - g[f"cov_{tag}"]).max() <= 1e-12 * scale
+        assert np.abs(corr - g[f"corr_{tag}"]).max() <= 1e-12
+        # rows >= N/step stay zero, result index is the window counter (sliding_windows.py:164-169)
+        assert np.all(cov[int(y.shape[0] / step):] == 0)
+
+
+def test_cv_oracle_matches_reference_fixtures():
+    g = np.load(os.path.join(GOLD, "sliding_cv.npz"))
+    assert tuple(g["bounds_1200"]) == (21, 181)  # SURVEY.md finding 2
+    for tag in "ab":
+        y = g[f"y_{tag}"]
+        assert so.cv_bounds(y.shape[0]) == tuple(int(v) for v in g[f"bounds_{tag}"])
+        windows, locs, table = so.cross_validated_table(y)
+        assert np.array_equal(windows, g[f"windows_{tag}"]) and np.array_equal(locs, g[f"locs_{tag}"])
+        ref = g[f"table_{tag}"]
+        assert np.array_equal(np.isinf(table), np.isinf(ref))
+        fin = np.isfinite(ref)
+        # w - 2 == D windows are barely full rank (cond ~ 1e10): eigh-driver differences show up at 1e-9
+        assert np.all(np.abs(table[fin] - ref[fin]) <= 1e-7 * np.abs(ref[fin]))
+        assert so.optimal_window_length(windows, table) == int(g[f"best_{tag}"])
+    assert np.isinf(g["table_b"]).any()  # D=25: short windows are rank deficient -> -inf (finding 3)
+
+
+def test_static_fc_known_answers():
+    """The reference's only exact golden vectors on this path
+    (tests/fcest/models/test_sliding_windows.py:25-44): np.cov on 3x2 integer data."""
+    y = np.array([[1.0, 2.0], [3.0, 5.0], [8.0, 9.0]])
+    c = so.np_cov_rows(y)
+    assert np.allclose(c, np.cov(y.T), rtol=0, atol=1e-15)
+    r = so.correlation_from_covariance(np.eye(3))
+    assert np.array_equal(r, np.eye(3))  # unit variance: cov == corr (test_array_operations.py:67-88)
+
+
+def test_mvn_logpdf_restatement_matches_scipy():
+    from scipy.stats import multivariate_normal
+    rng = np.random.default_rng(0)
+    for d, n in [(3, 10), (6, 5), (4, 30)]:
+        rows = rng.standard_normal((n, d))
+        cov = so.np_cov_rows(rows)
+        x = rng.standard_normal(d)
+        a = so.mvn_logpdf_allow_singular(x, cov)
+        b = multivariate_normal.logpdf(x, mean=np.zeros(d), cov=cov, allow_singular=True)
+        assert (np.isinf(a) and np.isinf(b)) or abs(a - b) <= 1e-10 * abs(b)
+
+
+# ---- Wishart oracle: regression fixtures, identities, gradient routes -------------------------------
+@pytest.mark.parametrize("tag,kind", [("svgp", "svgp"), ("vgp", "vgp")])
+def test_wishart_oracle_regression_fixture(tag, kind):
+    g = np.load(os.path.join(GOLD, "wishart_oracle.npz"))
+    N, D, S, M = (int(v) for v in g[f"{tag}_shape"])
+    x, y, eps, p = wo.make_inputs(N, D, S, M=None if M < 0 else M, seed=5)
+    elbo, grads = wo.elbo_and_grad(kind, p, x, y, eps)
+    assert abs(elbo - float(g[f"{tag}_elbo"])) <= 1e-12 * abs(elbo)
+    for k, v in grads.items():
+        ref = g[f"{tag}_grad_{k}"]
+        assert np.abs(v.numpy() - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-30), k
+
+
+def test_reference_likelihood_identities():
+    """tests/fcest/models/test_likelihoods.py:54-76 (matmul form, no additive noise):
+    L L^T = Sigma, 2 sum log diag L = logdet Sigma, |L^-1 y|^2 = y^T Sigma^-1 y."""
+    rng = np.random.default_rng(1)
+    S, N, D, nu = 2, 6, 2, 3
+    F = torch.tensor(rng.random((S, N, D, nu)))
+    A = torch.tensor(rng.random((D, D)))
+    y = torch.tensor(rng.random((N, D)))
+    AF = A @ F
+    Sig = AF @ AF.transpose(-1, -2)
+    L = torch.linalg.cholesky(Sig)
+    assert torch.allclose(L @ L.transpose(-1, -2), Sig, atol=1e-12)
+    assert torch.allclose(2 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1), torch.logdet(Sig), atol=1e-10)
+    z = torch.linalg.solve_triangular(L, y[None, :, :, None].expand(S, -1, -1, -1), upper=False)
+    q1 = (z ** 2).sum((2, 3))
+    q2 = (y[None, :, None, :] @ torch.linalg.inv(Sig) @ y[None, :, :, None])[..., 0, 0]
+    assert torch.allclose(q1, q2, rtol=1e-8)
+    # and the oracle's log_prob with a_matmul=True equals the dense MVN density built from those pieces
+    lam = torch.full((D,), -50.0, dtype=torch.float64)
+    lp = wo.log_prob(F, y, A, lam, a_matmul=True)
+    Sig2 = Sig + torch.diag_embed(torch.nn.functional.softplus(lam).expand(S, N, D))
+    ref = (-0.5 * D * np.log(2 * np.pi) - 0.5 * torch.logdet(Sig2)
+           - 0.5 * (y[None, :, None, :] @ torch.linalg.inv(Sig2) @ y[None, :, :, None])[..., 0, 0]).mean(0)
+    assert torch.allclose(lp, ref, rtol=1e-9)
+
+
+def test_closed_form_likelihood_gradient_matches_autograd():
+    x, y, eps, p = wo.make_inputs(20, 4, 3, M=8, seed=2)
+    fm, fv = wo.svgp_predict_f(x, p)
+    fm = fm.clone().requires_grad_(); fv = fv.clone().requires_grad_()
+    A = p["A"].clone().requires_grad_(); lam = p["lam"].clone().requires_grad_()
+    wo.variational_expectations(fm, fv, y, A, lam, eps).sum().backward()
+    cf = wo.likelihood_closed_form_grad(fm.detach(), fv.detach(), y, A.detach(), lam.detach(), eps)
+    for a, b in zip(cf, (fm.grad, fv.grad, A.grad, lam.grad)):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-12
+
+
+def test_oracle_gradient_finite_differences():
+    x, y, eps, p = wo.make_inputs(12, 3, 2, M=6, seed=4)
+    _, g = wo.elbo_and_grad("svgp", p, x, y, eps)
+    h = 1e-6
+    for name, idx in [("q_mu", (2, 4)), ("q_sqrt", (3, 4, 1)), ("A", (1, 2)), ("lam", (1,)), ("Z", (2, 0)),
+                      ("u_ls", (0,)), ("u_var", (0,))]:
+        pp = {k: v.clone() for k, v in p.items()}
+        pm = {k: v.clone() for k, v in p.items()}
+        pp[name][idx] += h
+        pm[name][idx] -= h
+        fd = (float(wo.svgp_elbo(pp, x, y, eps)) - float(wo.svgp_elbo(pm, x, y, eps))) / (2 * h)
+        an = float(g[name][idx])
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (name, fd, an)
+
+
+def test_chunked_oracle_equals_full():
+    x, y, eps, p = wo.make_inputs(30, 3, 3, M=10, seed=1)
+    e1, g1 = wo.elbo_and_grad("svgp", p, x, y, eps)
+    e2, g2 = wo.svgp_elbo_and_grad_chunked(p, x, y, eps, chunk=4)
+    assert abs(e1 - e2) <= 1e-12 * abs(e1)
+    for k in g1:
+        assert float((g1[k] - g2[k]).abs().max()) <= 1e-9 * max(float(g1[k].abs().max()), 1.0)
