@@ -39,10 +39,8 @@ def algorithmic_flops(N, D, S, M):
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    from fcest_b200.parallel import dist_env as _env
+    return _env()
 
 
 # ------------------------------------------------------------------------------------------------
