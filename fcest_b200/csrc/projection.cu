@@ -169,6 +169,208 @@ tri_grad_kernel(const double* __restrict__ Gk, long long ldk, const double* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Output-stationary variants of the two kernels above for M <= 200 (the SVGP default M = 200):
+// one CTA (16 warps) per latent keeps ALL lower 8x8 output tiles of the M x M result in registers
+// (pairs of horizontally adjacent tiles dealt cyclically to warps: balanced triangular work, the A
+// fragment is shared inside a pair) and streams the operands through shared memory in k-panels of 24
+// columns with a double-buffered cp.async pipeline, so q_sqrt / Gk are read from HBM exactly once.
+//   tri_syrk : S[ib][jb]   = sum_{kb <= jb} L[ib][kb] L[jb][kb]^T
+//   tri_grad : out[ib][jb] = sum_{kb >= jb} Gs[ib][kb] L[kb][jb]   (Gs = symmetric unpack of Gk)
+//              dq_sqrt = tril(out + diag(Gk_ii) L - kl L) + kl diag(1/L_mm)      (2 W = Gs + diag(Gk_ii))
+// ---------------------------------------------------------------------------------------------
+constexpr int TRI_WARPS = 16;
+constexpr int TRI_KP = 24;          // panel width (3 blocks of 8)
+constexpr int TRI_PITCH = TRI_KP + 4;
+constexpr int TRI_MAXPAIRS = 11;    // ceil(169 / 16) pairs per warp at nb = 25
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// pair u (row-major over rows ib with (ib+2)/2 pairs each) -> (ib, jb0)
+__device__ __forceinline__ int tri_pair_decode(int u) {
+  // rows 2a and 2a+1 both have a+1 pairs; pairs before row ib: (ib/2)(ib/2+1) + (ib odd ? ib/2+1 : 0)
+  int ib = (int)sqrtf((float)u) * 2;
+  while (true) {
+    const int h = ib >> 1;
+    const int before = h * (h + 1) + ((ib & 1) ? h + 1 : 0);
+    const int cnt = h + 1;
+    if (u < before) { ib -= 1; continue; }
+    if (u >= before + cnt) { ib += 1; continue; }
+    return (ib << 8) | (2 * (u - before));
+  }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(TRI_WARPS * 32, 1)
+tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __restrict__ Gk,
+                      double* __restrict__ out_packed, long long ldk, double* __restrict__ klp,
+                      double* __restrict__ dq_sqrt, double kl) {
+  extern __shared__ __align__(16) double sm[];
+  const int Mp = (M + 7) / 8 * 8, nb = Mp / 8;
+  const int PL = Mp + 4;                                   // pitch of the L row panel (GRAD)
+  const int stage_doubles = Mp * TRI_PITCH + (GRAD ? TRI_KP * PL : 0);
+  const int r = blockIdx.x;
+  const double* __restrict__ L = q_sqrt + (long long)r * M * M;
+  const double* __restrict__ G = GRAD ? Gk + (long long)r * ldk : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int npairs = (nb / 2) * (nb / 2 + 1) + ((nb & 1) ? nb / 2 + 1 : 0);
+  const int npanels = (nb + 2) / 3;
+
+  // (ib, jb0) of this warp's pairs, 10 bits each (ib << 5 | jb0; 1023 = none), three per register
+  unsigned pairs3[(TRI_MAXPAIRS + 2) / 3];
+  double acc[TRI_MAXPAIRS][2][2];
+#pragma unroll
+  for (int q = 0; q < (TRI_MAXPAIRS + 2) / 3; ++q) pairs3[q] = 0;
+#pragma unroll
+  for (int q = 0; q < TRI_MAXPAIRS; ++q) {
+    const int u = warp + q * TRI_WARPS;
+    unsigned code = 1023u;
+    if (u < npairs) { const int d = tri_pair_decode(u); code = (unsigned)(((d >> 8) << 5) | (d & 255)); }
+    pairs3[q / 3] |= code << (10 * (q % 3));
+    acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0;
+  }
+
+  // zero both stages once: rows >= M (padding) are never written by the loaders
+  for (int e = tid; e < 2 * stage_doubles; e += blockDim.x) sm[e] = 0.0;
+  __syncthreads();
+
+  auto load_panel = [&](int pnl, int buf) {
+    double* Wc = sm + buf * stage_doubles;                 // Mp x TRI_PITCH: column slab (L for syrk, Gs for grad)
+    const int k0 = pnl * TRI_KP;
+    if (!GRAD) {
+      // rows i >= k0 of L[:, k0:k0+24): 12 x 16-byte chunks per row (M even), zero-filled past column M
+      const int i0 = k0;
+      for (int e = tid; e < (M - i0) * (TRI_KP / 2); e += blockDim.x) {
+        const int i = i0 + e / (TRI_KP / 2), c2 = 2 * (e % (TRI_KP / 2)), k = k0 + c2;
+        int bytes = (M - k) * 8;
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        cp_async16(Wc + i * TRI_PITCH + c2, bytes > 0 ? L + (long long)i * M + k : L, bytes);
+      }
+    } else {
+      for (int e = tid; e < M * TRI_KP; e += blockDim.x) {
+        const int i = e / TRI_KP, kk = e - i * TRI_KP, k = k0 + kk;
+        double* dst = Wc + i * TRI_PITCH + kk;
+        if (k < M) {
+          const int idx = (k <= i) ? i * (i + 1) / 2 + k : k * (k + 1) / 2 + i;
+          cp_async8(dst, G + idx);
+        } else {
+          *dst = 0.0;
+        }
+      }
+      double* Lr = Wc + Mp * TRI_PITCH;                    // TRI_KP x PL: row panel of L (cols <= row)
+      const int rows = min(TRI_KP, M - k0);
+      for (int e = tid; e < rows * (Mp / 2); e += blockDim.x) {
+        const int kk = e / (Mp / 2), j = 2 * (e % (Mp / 2)), k = k0 + kk;
+        int bytes = (min(M, k + 1) - j) * 8;                // only columns j <= k (and < M) are non-zero
+        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+        cp_async16(Lr + kk * PL + j, bytes > 0 ? L + (long long)k * M + j : L, bytes);
+      }
+      for (int e = tid; e < (TRI_KP - rows) * Mp; e += blockDim.x)
+        Lr[(rows + e / Mp) * PL + e % Mp] = 0.0;
+    }
+    cp_async_commit();
+  };
+  // strict-upper entries of the slab's diagonal square must read as zero (L lower triangular)
+  auto mask_diag = [&](int pnl, int buf) {
+    if (GRAD) return;                                       // grad: Lr is masked by the copy sizes above
+    double* Wc = sm + buf * stage_doubles;
+    const int k0 = pnl * TRI_KP;
+    for (int e = tid; e < TRI_KP * TRI_KP; e += blockDim.x) {
+      const int ii = e / TRI_KP, kk = e - ii * TRI_KP;
+      if (kk > ii && k0 + ii < Mp) Wc[(k0 + ii) * TRI_PITCH + kk] = 0.0;
+    }
+  };
+
+  load_panel(0, 0);
+  for (int pnl = 0; pnl < npanels; ++pnl) {
+    const int buf = pnl & 1;
+    if (pnl + 1 < npanels) load_panel(pnl + 1, buf ^ 1); else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    mask_diag(pnl, buf);
+    if (!GRAD) __syncthreads();
+    const double* Wc = sm + buf * stage_doubles;
+    const double* Lr = Wc + Mp * TRI_PITCH;
+    const int kb_lo = 3 * pnl, kb_hi = min(nb, 3 * pnl + 3) - 1;   // blocks of this panel (inclusive)
+#pragma unroll
+    for (int q = 0; q < TRI_MAXPAIRS; ++q) {
+      const unsigned pr = (pairs3[q / 3] >> (10 * (q % 3))) & 1023u;
+      if (pr == 1023u) continue;
+      const int ib = pr >> 5, jb0 = pr & 31;
+      const bool two = (jb0 + 1 <= ib);
+      // syrk: tile (ib,jb) takes kb <= jb ; grad: kb >= jb   (block ranges, inclusive)
+      const int lo0 = GRAD ? max(kb_lo, jb0) : kb_lo, hi0 = GRAD ? kb_hi : min(kb_hi, jb0);
+      const int lo1 = GRAD ? max(kb_lo, jb0 + 1) : kb_lo, hi1 = GRAD ? kb_hi : min(kb_hi, jb0 + 1);
+      const int lo = min(lo0, lo1), hi = two ? max(hi0, hi1) : hi0;
+      if (lo > hi) continue;
+      const double* pa = Wc + (8 * ib + gid) * TRI_PITCH + tig - 8 * kb_lo;
+      const double* pb = GRAD ? Lr + (tig - 8 * kb_lo) * PL + 8 * jb0 + gid
+                              : Wc + (8 * jb0 + gid) * TRI_PITCH + tig - 8 * kb_lo;
+      for (int kb = lo; kb <= hi; ++kb) {
+        const bool u0 = (kb >= lo0 && kb <= hi0), u1 = two && (kb >= lo1 && kb <= hi1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ko = 8 * kb + 4 * h;
+          const double a = pa[ko];
+          if (u0) dmma(acc[q][0][0], acc[q][0][1], a, GRAD ? pb[ko * PL] : pb[ko]);
+          if (u1) dmma(acc[q][1][0], acc[q][1][1], a, GRAD ? pb[ko * PL + 8] : pb[ko + 8 * TRI_PITCH]);
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with `buf` before it is refilled two iterations later
+  }
+
+  // epilogue
+  double tr = 0.0;
+#pragma unroll
+  for (int q = 0; q < TRI_MAXPAIRS; ++q) {
+    const unsigned pr = (pairs3[q / 3] >> (10 * (q % 3))) & 1023u;
+    if (pr == 1023u) continue;
+    const int ib = pr >> 5, jb0 = pr & 31;
+    const int row = 8 * ib + gid;
+    if (row >= M) continue;
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2) {
+      if (jb0 + t2 > ib) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * (jb0 + t2) + 2 * tig + e;
+        if (col > row) continue;
+        const double c = acc[q][t2][e];
+        if (!GRAD) {
+          out_packed[(long long)r * ldk + (long long)row * (row + 1) / 2 + col] = c;
+          if (col == row) tr += c;
+        } else {
+          const double l = L[(long long)row * M + col];
+          double v = c + G[(long long)row * (row + 1) / 2 + row] * l - kl * l;
+          if (col == row) v += kl / l;
+          dq_sqrt[(long long)r * M * M + (long long)row * M + col] = v;
+        }
+      }
+    }
+  }
+  if (!GRAD) {
+    __shared__ double red[32];
+    const long long K = (long long)M * (M + 1) / 2;
+    for (long long idx = K + tid; idx < ldk; idx += blockDim.x) out_packed[(long long)r * ldk + idx] = 0.0;
+    double ld = 0.0;
+    for (int m = tid; m < M; m += blockDim.x) { const double d = L[(long long)m * M + m]; ld += log(d * d); }
+    tr = block_sum(tr, red);
+    ld = block_sum(ld, red);
+    if (tid == 0) { klp[2 * r] = tr; klp[2 * r + 1] = ld; }
+  } else {
+    // strict upper triangle of dq_sqrt is zero
+    double* o = dq_sqrt + (long long)r * M * M;
+    for (int e = tid; e < M * M; e += blockDim.x) {
+      const int i = e / M, j = e - i * M;
+      if (j > i) o[e] = 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dP[:, n] (+)= 2 T_n p_n - 2 gs[n] p_n * use_prior,   T_n symmetric from packed Tk[n, idx(i,j)].
 // gs[n] = sum_r g_var[n, r] (row sums, computed here).   grid = N, block = 256, smem = 2M + 32
 // ---------------------------------------------------------------------------------------------
@@ -229,6 +431,15 @@ extern "C" int fcest_pack_outer(const double* P, long long ldp, int M, int N, do
 extern "C" int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* Sk, long long ldk,
                                    double* kl_parts, cudaStream_t stream) {
   if (R <= 0) return 0;
+  if (M <= 200 && (M & 1) == 0) {
+    const int Mp = (M + 7) / 8 * 8;
+    const size_t smem = sizeof(double) * 2 * (size_t)Mp * TRI_PITCH;
+    cudaError_t e = cudaFuncSetAttribute(tri_stationary_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tri_stationary_kernel<false><<<R, TRI_WARPS * 32, smem, stream>>>(q_sqrt, M, nullptr, Sk, ldk, kl_parts, nullptr, 0.0);
+    FCEST_CHECK_LAUNCH();
+    return 0;
+  }
   tri_syrk_pack_kernel<<<R, 256, 0, stream>>>(q_sqrt, M, Sk, ldk, kl_parts);
   FCEST_CHECK_LAUNCH();
   return 0;
@@ -237,6 +448,15 @@ extern "C" int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* S
 extern "C" int fcest_tri_grad(const double* Gk, long long ldk, const double* q_sqrt, int R, int M,
                               double* dq_sqrt, double kl, cudaStream_t stream) {
   if (R <= 0) return 0;
+  if (M <= 200 && (M & 1) == 0) {
+    const int Mp = (M + 7) / 8 * 8;
+    const size_t smem = sizeof(double) * 2 * ((size_t)Mp * TRI_PITCH + (size_t)TRI_KP * (Mp + 4));
+    cudaError_t e = cudaFuncSetAttribute(tri_stationary_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tri_stationary_kernel<true><<<R, TRI_WARPS * 32, smem, stream>>>(q_sqrt, M, Gk, nullptr, ldk, nullptr, dq_sqrt, kl);
+    FCEST_CHECK_LAUNCH();
+    return 0;
+  }
   tri_grad_kernel<<<R, 256, 0, stream>>>(Gk, ldk, q_sqrt, M, dq_sqrt, kl);
   FCEST_CHECK_LAUNCH();
   return 0;
