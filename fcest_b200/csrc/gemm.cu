@@ -30,10 +30,7 @@ struct GemmParams {
   double* ws;  // split-K partials [splitk][M][ldc]
 };
 
-constexpr int BK = 16;
-constexpr int STAGES = 4;
-
-template <int BMN, bool KMAJOR>
+template <int BMN, int BK, bool KMAJOR>
 struct TileLayout {
   static constexpr int PITCH = KMAJOR ? (BK + 4) : (BMN + 4);
   static constexpr int ROWS = KMAJOR ? BMN : BK;
@@ -41,18 +38,18 @@ struct TileLayout {
 };
 
 // Load one BMN x BK operand tile with 16-byte cp.async; out-of-range elements are zero-filled.
-template <int BMN, bool KMAJOR, int NTHREADS>
+template <int BMN, int BK, bool KMAJOR, int NTHREADS>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, long long ld,
                                           int mn0, int MN, int k0, int kend, int tid) {
   constexpr int CHUNKS = BMN * BK / 2;
   constexpr int PER = (CHUNKS + NTHREADS - 1) / NTHREADS;
-  using L = TileLayout<BMN, KMAJOR>;
+  using L = TileLayout<BMN, BK, KMAJOR>;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int c = tid + i * NTHREADS;
     if (CHUNKS % NTHREADS != 0 && c >= CHUNKS) break;
     if (KMAJOR) {
-      const int row = c >> 3, kc = (c & 7) * 2;
+      const int row = c / (BK / 2), kc = (c % (BK / 2)) * 2;
       const int gm = mn0 + row, gk = k0 + kc;
       int bytes = (gm < MN) ? (kend - gk) * 8 : 0;
       bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
@@ -69,13 +66,14 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
   }
 }
 
-template <int BM, int BN, int WM, int WN, bool A_KMAJOR, bool B_KMAJOR>
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1)
 dgemm_dmma_kernel(const GemmParams p) {
   constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
   constexpr int TM = WM / 8, TN = WN / 8;
-  using LA = TileLayout<BM, A_KMAJOR>;
-  using LB = TileLayout<BN, B_KMAJOR>;
+  constexpr int KS = BK / 4;  // k4-steps per tile (even)
+  using LA = TileLayout<BM, BK, A_KMAJOR>;
+  using LB = TileLayout<BN, BK, B_KMAJOR>;
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
   double* sB = smem + STAGES * LA::DOUBLES;
@@ -83,7 +81,14 @@ dgemm_dmma_kernel(const GemmParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int wm = warp / (BN / WN), wn = warp % (BN / WN);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // 1-D tile index, fastest along the dimension with fewer tiles: the ~148 CTAs resident at any time
+  // then cover all of the short dimension and only a few tiles of the long one, so both operand
+  // panels of a wave stay L2 resident (DRAM traffic ~ algorithmic instead of one re-read per tile row).
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  int tm, tn;
+  if (tiles_m <= tiles_n) { tm = blockIdx.x % tiles_m; tn = blockIdx.x / tiles_m; }
+  else { tn = blockIdx.x % tiles_n; tm = blockIdx.x / tiles_n; }
+  const int m0 = tm * BM, n0 = tn * BN;
 
   int z = blockIdx.z;
   int kbeg = 0, kend = p.K;
@@ -131,8 +136,8 @@ dgemm_dmma_kernel(const GemmParams p) {
   auto issue_tile = [&](int t) {
     if (t < ktiles) {
       const int s = t % STAGES;
-      load_tile<BM, A_KMAJOR, NTHREADS>(sA + s * LA::DOUBLES, A, p.lda, m0, p.M, kbeg + t * BK, kend, tid);
-      load_tile<BN, B_KMAJOR, NTHREADS>(sB + s * LB::DOUBLES, B, p.ldb, n0, p.N, kbeg + t * BK, kend, tid);
+      load_tile<BM, BK, A_KMAJOR, NTHREADS>(sA + s * LA::DOUBLES, A, p.lda, m0, p.M, kbeg + t * BK, kend, tid);
+      load_tile<BN, BK, B_KMAJOR, NTHREADS>(sB + s * LB::DOUBLES, B, p.ldb, n0, p.N, kbeg + t * BK, kend, tid);
     }
     cp_async_commit();
   };
@@ -150,12 +155,11 @@ dgemm_dmma_kernel(const GemmParams p) {
 
   for (int kt = 0; kt < ktiles; ++kt) {
     const int slot = kt % STAGES;
-    load_frags(fa[1], fb[1], slot, 1);
-    mma_step(fa[0], fb[0]);
-    load_frags(fa[0], fb[0], slot, 2);
-    mma_step(fa[1], fb[1]);
-    load_frags(fa[1], fb[1], slot, 3);
-    mma_step(fa[0], fb[0]);
+#pragma unroll
+    for (int kk = 0; kk < KS - 1; ++kk) {
+      load_frags(fa[(kk + 1) & 1], fb[(kk + 1) & 1], slot, kk + 1);
+      mma_step(fa[kk & 1], fb[kk & 1]);
+    }
     if (kt + 1 < ktiles) {
       cp_async_wait<STAGES - 2>();  // tile kt+1 has landed (kt+2, kt+3 may still be in flight)
       __syncthreads();              // ... for every thread; nobody reads ring slot `slot` any more
@@ -222,19 +226,20 @@ __global__ void splitk_reduce_kernel(const GemmParams p) {
   }
 }
 
-template <int BM, int BN, int WM, int WN, bool AK, bool BKM>
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool AK, bool BKM>
 static int launch_cfg(const GemmParams& p, int batch, cudaStream_t stream) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr size_t smem =
-      sizeof(double) * STAGES * (TileLayout<BM, AK>::DOUBLES + TileLayout<BN, BKM>::DOUBLES);
-  auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, AK, BKM>;
+      sizeof(double) * STAGES * (TileLayout<BM, BK, AK>::DOUBLES + TileLayout<BN, BK, BKM>::DOUBLES);
+  static_assert(smem <= 227 * 1024, "tile ring exceeds shared memory");
+  auto kern = dgemm_dmma_kernel<BM, BN, WM, WN, BK, STAGES, AK, BKM>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splitk > 1 ? p.splitk : batch);
+  dim3 grid(((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM), 1, p.splitk > 1 ? p.splitk : batch);
   kern<<<grid, NT, smem, stream>>>(p);
   FCEST_CHECK_LAUNCH();
   if (p.splitk > 1) {
@@ -247,12 +252,12 @@ static int launch_cfg(const GemmParams& p, int batch, cudaStream_t stream) {
   return 0;
 }
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int BK, int STAGES>
 static int launch_layout(const GemmParams& p, int a_kmajor, int b_kmajor, int batch, cudaStream_t s) {
-  if (a_kmajor && b_kmajor) return launch_cfg<BM, BN, WM, WN, true, true>(p, batch, s);
-  if (a_kmajor && !b_kmajor) return launch_cfg<BM, BN, WM, WN, true, false>(p, batch, s);
-  if (!a_kmajor && b_kmajor) return launch_cfg<BM, BN, WM, WN, false, true>(p, batch, s);
-  return launch_cfg<BM, BN, WM, WN, false, false>(p, batch, s);
+  if (a_kmajor && b_kmajor) return launch_cfg<BM, BN, WM, WN, BK, STAGES, true, true>(p, batch, s);
+  if (a_kmajor && !b_kmajor) return launch_cfg<BM, BN, WM, WN, BK, STAGES, true, false>(p, batch, s);
+  if (!a_kmajor && b_kmajor) return launch_cfg<BM, BN, WM, WN, BK, STAGES, false, true>(p, batch, s);
+  return launch_cfg<BM, BN, WM, WN, BK, STAGES, false, false>(p, batch, s);
 }
 
 }  // namespace fcest
@@ -264,7 +269,8 @@ namespace fcest {
 //  * small problems use 64x64 tiles;
 //  * K is split only when the tile count leaves SMs idle (< 4 waves), because every split costs
 //    2 * M * N * 8 bytes of partial-tile traffic plus a reduce launch.
-struct GemmPlan { int cfg; int splitk; };  // cfg 0: 64x64, 1: 128x128, 2: 120x128
+struct GemmPlan { int cfg; int splitk; int bk; };  // cfg 0: 64x64x16, 1: 128x128x32, 2: 120x128x32
+constexpr int BK_SMALL = 16, BK_BIG = 32;
 
 static GemmPlan plan_gemm(int M, int N, int K, int batch) {
   const int sms = 148;
@@ -278,6 +284,8 @@ static GemmPlan plan_gemm(int M, int N, int K, int batch) {
     bm = pl.cfg == 2 ? 120 : 128;
   }
   const int bn = big ? 128 : 64;
+  const int BK = big ? BK_BIG : BK_SMALL;
+  pl.bk = BK;
   const long long tiles = (long long)((M + bm - 1) / bm) * ((N + bn - 1) / bn);
   int splitk = 1;
   if (batch == 1) {
@@ -299,6 +307,11 @@ static GemmPlan plan_gemm(int M, int N, int K, int batch) {
   return pl;
 }
 }  // namespace fcest
+
+#ifdef FCEST_GEMM_EXPERIMENTS
+static int g_force_cfg = 0;
+extern "C" void fcest_dgemm_force_cfg(int cfg) { g_force_cfg = cfg; }
+#endif
 
 extern "C" long long fcest_dgemm_workspace_bytes(int M, int N, int K, long long ldc, int batch) {
   const int splitk = fcest::plan_gemm(M, N, K, batch).splitk;
@@ -327,10 +340,17 @@ extern "C" int fcest_dgemm(int a_kmajor, int b_kmajor, int M, int N, int K, doub
   if (splitk > 1 && (workspace == nullptr || workspace_bytes < (long long)splitk * M * ldc * 8))
     splitk = 1;  // no workspace supplied: run unsplit (still correct, just fewer CTAs)
   p.splitk = splitk;
-  const int ktiles = (K + BK - 1) / BK;
-  p.k_per_split = ((ktiles + splitk - 1) / splitk) * BK;
+  const int ktiles = (K + pl.bk - 1) / pl.bk;
+  p.k_per_split = ((ktiles + splitk - 1) / splitk) * pl.bk;
   p.ws = workspace;
-  if (pl.cfg == 2) return launch_layout<120, 128, 40, 32>(p, a_kmajor, b_kmajor, batch, stream);
-  if (pl.cfg == 1) return launch_layout<128, 128, 32, 32>(p, a_kmajor, b_kmajor, batch, stream);
-  return launch_layout<64, 64, 32, 32>(p, a_kmajor, b_kmajor, batch, stream);
+#ifdef FCEST_GEMM_EXPERIMENTS
+  if (g_force_cfg == 3) return launch_layout<120, 128, 40, 32, 16, 4>(p, a_kmajor, b_kmajor, batch, stream);
+  if (g_force_cfg == 4) return launch_layout<128, 128, 32, 32, BK_BIG, 3>(p, a_kmajor, b_kmajor, batch, stream);
+  if (g_force_cfg == 5) return launch_layout<120, 128, 40, 16, BK_BIG, 3>(p, a_kmajor, b_kmajor, batch, stream);
+  if (g_force_cfg == 6) return launch_layout<128, 128, 64, 32, BK_BIG, 3>(p, a_kmajor, b_kmajor, batch, stream);
+  if (g_force_cfg == 7) return launch_layout<120, 128, 40, 64, BK_BIG, 3>(p, a_kmajor, b_kmajor, batch, stream);
+#endif
+  if (pl.cfg == 2) return launch_layout<120, 128, 40, 32, BK_BIG, 3>(p, a_kmajor, b_kmajor, batch, stream);
+  if (pl.cfg == 1) return launch_layout<128, 128, 32, 32, BK_BIG, 3>(p, a_kmajor, b_kmajor, batch, stream);
+  return launch_layout<64, 64, 32, 32, BK_SMALL, 4>(p, a_kmajor, b_kmajor, batch, stream);
 }
