@@ -23,8 +23,9 @@ _d = C.c_double
 # name -> (restype, argtypes).  Kept in lock-step with include/fcest_b200.h (tests/test_abi.py checks).
 SIGNATURES = {
     "fcest_wishart_loglik_smem_bytes": (_ll, [_i, _i]),
+    "fcest_wishart_loglik_scratch_bytes": (_ll, [_i, _i]),
     "fcest_wishart_loglik": (_i, [_p, _p, _ll, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _ll, _p, _p,
-                                  _p, _p, _p, _p]),
+                                  _p, _p, _p, _p, _p]),
     "fcest_dgemm_workspace_bytes": (_ll, [_i, _i, _i, _ll, _i]),
     "fcest_dgemm": (_i, [_i, _i, _i, _i, _i, _d, _p, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _ll, _p, _p, _i,
                          _p, _ll, _p]),
@@ -46,9 +47,10 @@ SIGNATURES = {
     "fcest_softplus_bwd": (_i, [_p, _p, _p, _i, _p]),
     "fcest_adam_step": (_i, [_p, _p, _p, _p, _ll, _d, _ll, _d, _d, _d, _d, _p]),
     "fcest_randn": (_i, [_p, _ll, _ull, _ull, _p]),
+    "fcest_cov_moments_scratch_bytes": (_ll, [_i, _i]),
     "fcest_cov_moments": (_i, [_p, _p, _ll, _p, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _p, _p, _p, _i, _p, _p,
-                               _p]),
-    "fcest_batched_chol_info": (_i, [_p, _i, _i, _d, _p, _p]),
+                               _p, _p]),
+    "fcest_batched_chol_info": (_i, [_p, _i, _i, _d, _p, _p, _p]),
     "fcest_window_cov": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fcest_window_cv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _d, _p, _ll, _p]),
     "fcest_launch_count": (_ll, []),

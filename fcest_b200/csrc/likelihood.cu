@@ -37,12 +37,19 @@ struct LikParams {
   double* glam_part;  // (N, D)
   int* info;          // (N,) 0 = ok, else 1-based index of the first non-positive pivot (any sample)
   int need_grad;
+  double* ws; long long ws_stride;  // BIG variant: per-CTA global scratch for G, T, Yb
 };
 
 
 // One CTA (8 warps) per time step; per MC sample a blocked (8x8 tiles) Cholesky / inverse on the fp64
 // tensor pipe.  Shared memory: G (D x nu, later H = Li G, then Q = Sigma^-1 G, in place per column
 // block), T (lower: Sigma -> L; strict upper: Li^T), a y column block and per-warp scratch tiles.
+// BIG = false: the whole problem lives in shared memory (D <= ~80), one CTA per time step.
+// BIG = true : G, T and the y block live in a per-CTA slot of an L2-resident global workspace (same
+//              tile algorithm, block / warp barriers order the global accesses inside the CTA); a
+//              persistent grid walks the time steps.  Functional path for D up to 400; a cluster /
+//              TMA-staged variant is the planned replacement.
+template <bool BIG>
 __global__ void __launch_bounds__(256, 3)
 wishart_loglik_kernel(const LikParams p) {
   extern __shared__ __align__(16) double sm[];
@@ -50,10 +57,11 @@ wishart_loglik_kernel(const LikParams p) {
   const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
   const int Pd = pitch4(Dp), Pg = pitch4(Np);
   const int nbD = Dp / 8, nbN = Np / 8;
-  double* G = sm;                 // Dp x Pg
+  double* big = BIG ? p.ws + (long long)blockIdx.x * p.ws_stride : sm;
+  double* G = big;                // Dp x Pg
   double* T = G + Dp * Pg;        // Dp x Pd
   double* Yb = T + Dp * Pd;       // Dp x 12 : column 0 = y -> z -> alpha
-  double* scr = Yb + Dp * 12;     // 8 warps x 96
+  double* scr = BIG ? sm : Yb + Dp * 12;  // 8 warps x 96
   double* dinv = scr + 8 * 96;    // Dp  1 / L_dd
   double* yv = dinv + Dp;         // Dp
   double* spl = yv + Dp;          // Dp  softplus(lam)
@@ -62,15 +70,16 @@ wishart_loglik_kernel(const LikParams p) {
   double* scal = cv + Np;         // [0] = |z|^2
   __shared__ int bad_s;
 
-  const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int nwarps = 8;
   const int gid = lane >> 2, tig = lane & 3;
   const double w = 1.0 / p.S;
-  const double* fm = p.fmean + (long long)n * p.ldf;
-  const double* fv = p.fvar + (long long)n * p.ldf;
   double* myscr = scr + warp * 96;
 
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+  const double* fm = p.fmean + (long long)n * p.ldf;
+  const double* fv = p.fvar + (long long)n * p.ldf;
+  __syncthreads();
   for (int d = tid; d < Dp; d += blockDim.x) {
     yv[d] = d < D ? p.y[(long long)n * D + d] : 0.0;
     spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
@@ -256,6 +265,7 @@ wishart_loglik_kernel(const LikParams p) {
     p.ve[n] = bad_s ? nan("") : ve_acc;
     p.info[n] = bad_s;
   }
+  }  // time-step loop
 }
 
 // out[c] = sum_{row} X[row, c] in a fixed (deterministic) order; block = (32 columns) x (32 row lanes).
@@ -290,25 +300,46 @@ extern "C" long long fcest_wishart_loglik_smem_bytes(int D, int nu) {
   return (long long)sizeof(double) * ((long long)Dp * Pg + (long long)Dp * Pd + 12LL * Dp + 8 * 96 + 4 * Dp + Np + 8);
 }
 
+// Large-D variant: number of persistent CTAs and bytes of global scratch the caller must provide
+// (0 when the problem fits shared memory and no scratch is needed).
+static const int kBigCtas = 148 * 3;
+extern "C" long long fcest_wishart_loglik_scratch_bytes(int D, int nu) {
+  if (fcest_wishart_loglik_smem_bytes(D, nu) <= 227 * 1024) return 0;
+  const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
+  const long long stride = (long long)Dp * pitch4(Np) + (long long)Dp * pitch4(Dp) + 12LL * Dp;
+  return (long long)sizeof(double) * stride * kBigCtas;
+}
+
 extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, long long ldf,
                                     const double* eps, const double* y, const double* A, int a_mode,
                                     const double* lam, int S, int N, int D, int nu, double* ve,
                                     double* g_fmean, double* g_fvar, long long ldg, double* gA,
                                     double* glam, double* ws_gA_part, double* ws_glam_part,
-                                    int* info, cudaStream_t stream) {
+                                    int* info, double* scratch, cudaStream_t stream) {
   if (N <= 0) return 0;
-  const long long smem = fcest_wishart_loglik_smem_bytes(D, nu);
-  if (smem > 227 * 1024) return FCEST_ERR_UNSUPPORTED;
+  long long smem = fcest_wishart_loglik_smem_bytes(D, nu);
+  const bool bigD = smem > 227 * 1024;
+  if (D > 400 || nu > 400) return FCEST_ERR_UNSUPPORTED;
+  if (bigD && scratch == nullptr) return FCEST_ERR_ARGUMENT;
   LikParams p;
   p.fmean = fmean; p.fvar = fvar; p.ldf = ldf; p.eps = eps; p.y = y; p.A = A; p.a_mode = a_mode;
   p.lam = lam; p.S = S; p.N = N; p.D = D; p.nu = nu; p.ve = ve; p.g_fmean = g_fmean;
   p.g_fvar = g_fvar; p.ldg = ldg; p.gA_part = ws_gA_part; p.glam_part = ws_glam_part; p.info = info;
   p.need_grad = (g_fmean != nullptr);
   if (p.need_grad && (!g_fvar || !ws_gA_part || !ws_glam_part || !gA || !glam)) return FCEST_ERR_ARGUMENT;
-  cudaError_t e = cudaFuncSetAttribute(wishart_loglik_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  wishart_loglik_kernel<<<N, 256, smem, stream>>>(p);
+  p.ws = scratch;
+  p.ws_stride = 0;
+  if (!bigD) {
+    cudaError_t e = cudaFuncSetAttribute(wishart_loglik_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    wishart_loglik_kernel<false><<<N, 256, smem, stream>>>(p);
+  } else {
+    const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
+    p.ws_stride = (long long)Dp * pitch4(Np) + (long long)Dp * pitch4(Dp) + 12LL * Dp;
+    smem = sizeof(double) * (8 * 96 + 4 * Dp + Np + 8);
+    wishart_loglik_kernel<true><<<N < kBigCtas ? N : kBigCtas, 256, smem, stream>>>(p);
+  }
   FCEST_CHECK_LAUNCH();
   if (p.need_grad) {
     const int R = D * nu;

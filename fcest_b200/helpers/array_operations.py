@@ -51,7 +51,10 @@ def are_all_positive_definite(covariance_matrices) -> bool:
     t = t.to(device="cuda", dtype=torch.float64).contiguous()
     B, D = t.shape[0], t.shape[-1]
     info = torch.zeros(B, dtype=torch.int32, device=t.device)
-    ops.call("fcest_batched_chol_info", ops.ptr(t), B, D, 1e-8, ops.ptr(info))
+    scratch = None
+    if D * (D + 1) * 8 > 227 * 1024:
+        scratch = torch.empty(B * D * (D + 1), dtype=torch.float64, device=t.device)
+    ops.call("fcest_batched_chol_info", ops.ptr(t), B, D, 1e-8, ops.ptr(info), ops.ptr(scratch))
     info = info.cpu().numpy()
     if (info < 0).any():
         logging.warning('Matrix is not symmetric.')

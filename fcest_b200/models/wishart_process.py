@@ -21,7 +21,7 @@ import os
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..gp import conditionals as cond
 from ..gp.kernels import Kernel, Matern52
 from ..gp.parameter import Parameter
@@ -168,6 +168,8 @@ class _WishartProcessBase:
         out_mean = torch.empty((n, D, D), dtype=F64, device=dev)
         out_std = torch.empty((n, D, D), dtype=F64, device=dev)
         samples = torch.empty((num_mc_samples, n, D, D), dtype=F64, device=dev) if want_samples else None
+        nscr = int(_lib.load_library().fcest_cov_moments_scratch_bytes(D, self.nu))
+        scratch = torch.empty(nscr // 8, dtype=F64, device=dev) if nscr else None  # large-D tile scratch
         # stream the samples in chunks that keep the epsilon buffer around 256 MB
         chunk = num_mc_samples if epsilon is not None else max(1, min(num_mc_samples, (1 << 25) // max(n * R, 1)))
         done = 0
@@ -182,7 +184,7 @@ class _WishartProcessBase:
             ops.call("fcest_cov_moments", ops.ptr(f_mean_new), ops.ptr(f_variance_new), ops.ld(f_mean_new),
                      ops.ptr(eps), ops.ptr(A), a_mode, ops.ptr(lik.additive_part.unconstrained), sc, n, D,
                      self.nu, int(corr), done, ops.ptr(mean), ops.ptr(m2), ops.ptr(smp), int(last),
-                     ops.ptr(out_mean), ops.ptr(out_std))
+                     ops.ptr(out_mean), ops.ptr(out_std), ops.ptr(scratch))
             done += sc
         return out_mean, out_std, samples
 

@@ -145,9 +145,10 @@ def wishart_loglik(fmean, fvar, eps, y, A, lam, need_grad=True):
     assert eps.is_contiguous() and eps.shape == (S, N, R) and y.is_contiguous() and A.is_contiguous()
     assert ld(fmean) == ld(fvar)
     lib = _lib.load_library()
-    if lib.fcest_wishart_loglik_smem_bytes(D, nu) > 227 * 1024:
-        raise NotImplementedError(
-            f"fcest_b200: the shared-memory likelihood kernel supports D up to ~80 (got D={D}, nu={nu}).")
+    if D > 400:
+        raise NotImplementedError(f"fcest_b200: the likelihood kernels support D <= 400 (got D={D}).")
+    nscr = int(lib.fcest_wishart_loglik_scratch_bytes(D, nu))
+    scratch = torch.empty(nscr // 8, dtype=F64, device=dev) if nscr else None  # large-D tile scratch
     a_mode = 0 if A.dim() == 2 else 1
     ve = torch.empty(N, dtype=F64, device=dev)
     info = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -161,9 +162,9 @@ def wishart_loglik(fmean, fvar, eps, y, A, lam, need_grad=True):
         ws_l = torch.empty((N, D), dtype=F64, device=dev)
         call("fcest_wishart_loglik", ptr(fmean), ptr(fvar), ld(fmean), ptr(eps), ptr(y), ptr(A), a_mode,
              ptr(lam), S, N, D, nu, ptr(ve), ptr(g_fmean), ptr(g_fvar), ld(g_fmean), ptr(gA), ptr(glam),
-             ptr(ws_a), ptr(ws_l), ptr(info), flops=(3.0 * D * D * nu + 2.0 / 3.0 * D ** 3 + D * D) * S * N)
+             ptr(ws_a), ptr(ws_l), ptr(info), ptr(scratch), flops=(3.0 * D * D * nu + 2.0 / 3.0 * D ** 3 + D * D) * S * N)
         out.update(g_fmean=g_fmean, g_fvar=g_fvar, gA=gA, glam=glam)
     else:
         call("fcest_wishart_loglik", ptr(fmean), ptr(fvar), ld(fmean), ptr(eps), ptr(y), ptr(A), a_mode,
-             ptr(lam), S, N, D, nu, ptr(ve), None, None, 0, None, None, None, None, ptr(info))
+             ptr(lam), S, N, D, nu, ptr(ve), None, None, 0, None, None, None, None, ptr(info), ptr(scratch))
     return out

@@ -37,13 +37,16 @@ typedef struct CUstream_st* cudaStream_t;
  *   lam : (D,) unconstrained additive noise (softplus applied inside, likelihoods.py:253-264)
  *   ve : (N,) out, mean over samples of the Gaussian log density
  *   g_fmean, g_fvar : (N, R) pitch ldg, d sum(ve) / d fmean, fvar;  gA : (D,nu) or (nu,);  glam : (D,)
- *   ws_gA_part : (N, R) and ws_glam_part : (N, D) workspaces;  info : (N,) */
+ *   ws_gA_part : (N, R) and ws_glam_part : (N, D) workspaces;  info : (N,)
+ *   scratch : fcest_wishart_loglik_scratch_bytes(D, nu) bytes of global memory (0 / NULL while the D x D
+ *             problem fits shared memory, D <= ~80; the large-D variant, D <= 400, keeps its tiles there) */
 long long fcest_wishart_loglik_smem_bytes(int D, int nu);
+long long fcest_wishart_loglik_scratch_bytes(int D, int nu);
 int fcest_wishart_loglik(const double* fmean, const double* fvar, long long ldf, const double* eps,
                          const double* y, const double* A, int a_mode, const double* lam, int S,
                          int N, int D, int nu, double* ve, double* g_fmean, double* g_fvar,
                          long long ldg, double* gA, double* glam, double* ws_gA_part,
-                         double* ws_glam_part, int* info, cudaStream_t stream);
+                         double* ws_glam_part, int* info, double* scratch, cudaStream_t stream);
 
 /* ---- fp64 tensor-core GEMM (DMMA): C = alpha op(A) op(B) + beta C + bias_row[m] + bias_col[n].
  *      Replaces the tf.matmul calls inside gpflow.conditionals.util.base_conditional that
@@ -117,12 +120,15 @@ int fcest_randn(double* out, long long n, unsigned long long seed, unsigned long
  *   cov_moments streams Sc samples Sigma = (A o F)(A o F)^T + diag(softplus(lam)) (optionally converted
  *   to correlations) into a running Welford state (mean, m2: (N,D,D), cnt0 samples already folded);
  *   `samples` (Sc,N,D,D) optionally receives the raw samples; finalize writes mean and population std.
- *   batched_chol_info: the are_all_positive_definite() assertion: -1 = not symmetric, k>0 = not PD. */
+ *   batched_chol_info: the are_all_positive_definite() assertion: -1 = not symmetric, k>0 = not PD;
+ *   scratch = B*D*(D+1) doubles when D*(D+1)*8 exceeds shared memory (D > ~168), else NULL. */
+long long fcest_cov_moments_scratch_bytes(int D, int nu);
 int fcest_cov_moments(const double* fmean, const double* fvar, long long ldf, const double* eps,
                       const double* A, int a_mode, const double* lam, int Sc, int N, int D, int nu,
                       int corr, long long cnt0, double* mean, double* m2, double* samples,
-                      int finalize, double* out_mean, double* out_std, cudaStream_t stream);
-int fcest_batched_chol_info(const double* A, int B, int D, double atol, int* info,
+                      int finalize, double* out_mean, double* out_std, double* scratch,
+                      cudaStream_t stream);
+int fcest_batched_chol_info(const double* A, int B, int D, double atol, int* info, double* scratch,
                             cudaStream_t stream);
 
 /* ---- sliding windows: SlidingWindows.overlapping_windowed_cov_estimation

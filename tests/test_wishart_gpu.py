@@ -183,3 +183,40 @@ def test_adam_trajectory_parity(cuda):
     assert _rel(m.q_sqrt.unconstrained.cpu().numpy(), p["q_sqrt"].numpy()) < 1e-9
     assert _rel(m.likelihood.A_scale_matrix.unconstrained.cpu().numpy(), p["A"].numpy()) < 1e-9
     assert abs(m.kernel.lengthscales.unconstrained.item() - p["u_ls"].item()) < 1e-9
+
+
+def test_large_D_path(cuda):
+    """D > 80 uses the global-scratch variants of the likelihood / predict kernels."""
+    kind, N, D, S, M = "svgp", 12, 96, 2, 8
+    m, x, y, eps, p = _build(kind, N, D, S, M)
+    elbo_ref, g_ref = wo.elbo_and_grad(kind, p, x, y, eps)
+    elbo = m.elbo_and_grad((x.numpy(), y.numpy()), epsilon=eps.cuda()).item()
+    assert abs(elbo - elbo_ref) / abs(elbo_ref) < 1e-8, (elbo, elbo_ref)
+    for k, v in {"q_sqrt": m.q_sqrt.grad, "A": m.likelihood.A_scale_matrix.grad,
+                 "lam": m.likelihood.additive_part.grad, "q_mu": m.q_mu.grad}.items():
+        assert _rel(v.cpu().numpy().reshape(-1), g_ref[k].numpy().reshape(-1)) < 1e-7, k
+    xn = torch.linspace(0, 1, 5, dtype=torch.float64)[:, None]
+    fm_ref, fv_ref = wo.svgp_predict_f(xn, p)
+    g = torch.Generator().manual_seed(1)
+    eps_new = torch.randn(6, 5, D, D, dtype=torch.float64, generator=g)
+    cm_ref, cs_ref = wo.predict_cov(fm_ref, fv_ref, p["A"], p["lam"], eps_new, D)
+    rm_ref, rs_ref = wo.predict_corr(fm_ref, fv_ref, p["A"], p["lam"], eps_new, D)
+    cm, cs = m.predict_cov(xn.numpy(), 6, epsilon=eps_new.cuda())
+    rm, rs = m.predict_corr(xn.numpy(), 6, epsilon=eps_new.cuda())
+    for a, b in [(cm, cm_ref), (cs, cs_ref), (rm, rm_ref), (rs, rs_ref)]:
+        assert np.abs(a.cpu().numpy() - b.numpy()).max() < 1e-6 * max(1.0, float(b.abs().max()))
+
+
+def test_pd_check_large_and_truth_table(cuda):
+    """are_all_positive_definite: the reference's truth table (tests/fcest/helpers/test_array_operations.py:16-65)
+    and a D = 200 batch (global-scratch path)."""
+    from fcest_b200.helpers.array_operations import are_all_positive_definite
+    assert not are_all_positive_definite(np.array([[[1.0, 2.0], [2.0, 1.0]], [[1.0, 0.0], [0.0, 1.0]]]))
+    assert not are_all_positive_definite(np.array([[[1.0, 0.5], [0.4, 1.0]]]))
+    assert are_all_positive_definite(np.array([[[2.0, 0.5], [0.5, 1.0]], [[1.0, 0.0], [0.0, 1.0]]]))
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 200, 220))
+    spd = a @ np.swapaxes(a, 1, 2)
+    assert are_all_positive_definite(spd)
+    spd[1, 5, 5] = -1.0
+    assert not are_all_positive_definite(spd)
