@@ -26,67 +26,86 @@ window_cov_kernel(const double* __restrict__ y, int N, int D, int w, int step, i
   double* Xs = sm;              // wp x Pn, centred window (zero padded)
   double* mean = Xs + wp * Pn;  // Dp
   double* vd = mean + Dp;       // Dp: sqrt(diag(cov))
-  const int i = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  double* o = out + (long long)i * D * D;
-  if (i >= nwin) {  // rows >= int(N / step) stay zero (sliding_windows.py:164-165)
-    for (int e = tid; e < D * D; e += blockDim.x) o[e] = 0.0;
-    return;
-  }
-  const int pad = w / 2, start = i * step;
-  for (int e = tid; e < wp * Pn; e += blockDim.x) {
-    const int t = e / Pn, d = e - t * Pn;
-    double v = 0.0;
-    if (t < w && d < D) {
-      const int src = start + t - pad;
-      if (src >= 0 && src < N) v = y[(long long)src * D + d];
-    }
-    Xs[e] = v;
-  }
-  __syncthreads();
-  for (int d = tid; d < Dp; d += blockDim.x) {
-    double s = 0.0;
-    for (int t = 0; t < w; ++t) s += Xs[t * Pn + d];
-    mean[d] = s / w;
-  }
-  __syncthreads();
-  for (int e = tid; e < w * Pn; e += blockDim.x) {
-    const int d = e % Pn;
-    if (d < D) Xs[e] -= mean[d];
-  }
-  __syncthreads();
+  const int pad = w / 2;
   const double fact = 1.0 / (double)(w - 1);
-  if (corr) {
-    for (int d = tid; d < Dp; d += blockDim.x) {
-      double s = 0.0;
-      for (int t = 0; t < w; ++t) s += Xs[t * Pn + d] * Xs[t * Pn + d];
-      vd[d] = sqrt(s * fact);
+  const int nb = Dp / 8, ntiles = nb * (nb + 1) / 2;
+  const bool vec = ((D & 1) == 0);
+  // persistent over output windows: the grid is sized to one resident wave (see fcest_window_cov)
+  for (int i = blockIdx.x; i < N; i += gridDim.x) {
+    double* o = out + (long long)i * D * D;
+    if (i >= nwin) {  // rows >= int(N / step) stay zero (sliding_windows.py:164-165)
+      for (int e = tid; e < D * D; e += blockDim.x) o[e] = 0.0;
+      continue;
+    }
+    const int start = i * step;
+    __syncthreads();
+    for (int e = tid; e < wp * Pn; e += blockDim.x) {
+      const int t = e / Pn, d = e - t * Pn;
+      double v = 0.0;
+      if (t < w && d < D) {
+        const int src = start + t - pad;
+        if (src >= 0 && src < N) v = y[(long long)src * D + d];
+      }
+      Xs[e] = v;
     }
     __syncthreads();
-  }
-  const int nb = Dp / 8;
-  const bool vec = ((D & 1) == 0);
-  for (int t = warp; t < nb * nb; t += nwarps) {
-    const int ib = t / nb, jb = t - ib * nb;
-    double c0 = 0.0, c1 = 0.0;
-    const double* xa = Xs + tig * Pn + 8 * ib + gid;
-    const double* xb = Xs + tig * Pn + 8 * jb + gid;
-    for (int k0 = 0; k0 < wp; k0 += 4) dmma(c0, c1, xa[k0 * Pn], xb[k0 * Pn]);
-    const int row = 8 * ib + gid, col = 8 * jb + 2 * tig;
-    if (row >= D || col >= D) continue;
-    c0 *= fact;
-    c1 *= fact;
-    if (corr) {
-      c0 = (c0 == 0.0) ? 0.0 : c0 / (vd[row] * vd[col]);
-      if (col + 1 < D) c1 = (c1 == 0.0) ? 0.0 : c1 / (vd[row] * vd[col + 1]);
+    for (int d = tid; d < Dp; d += blockDim.x) {
+      double s = 0.0;
+      for (int t = 0; t < w; ++t) s += Xs[t * Pn + d];
+      mean[d] = s / w;
     }
-    double* dst = o + (long long)row * D + col;
-    if (vec && col + 1 < D) {
-      *reinterpret_cast<double2*>(dst) = make_double2(c0, c1);
-    } else {
-      dst[0] = c0;
-      if (col + 1 < D) dst[1] = c1;
+    __syncthreads();
+    for (int e = tid; e < w * Pn; e += blockDim.x) {
+      const int d = e % Pn;
+      if (d < D) Xs[e] -= mean[d];
+    }
+    __syncthreads();
+    if (corr) {
+      for (int d = tid; d < Dp; d += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < w; ++t) s += Xs[t * Pn + d] * Xs[t * Pn + d];
+        vd[d] = sqrt(s * fact);
+      }
+      __syncthreads();
+    }
+    // lower tiles only (the Gram matrix is symmetric); each tile is also stored transposed
+    for (int t = warp; t < ntiles; t += nwarps) {
+      int ib = 0, rem = t;
+      while (rem > ib) { rem -= ib + 1; ++ib; }
+      const int jb = rem;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: even / odd k4-steps
+      const double* xa = Xs + tig * Pn + 8 * ib + gid;
+      const double* xb = Xs + tig * Pn + 8 * jb + gid;
+      int k0 = 0;
+      for (; k0 + 4 < wp; k0 += 8) {
+        dmma(c0, c1, xa[k0 * Pn], xb[k0 * Pn]);
+        dmma(e0, e1, xa[(k0 + 4) * Pn], xb[(k0 + 4) * Pn]);
+      }
+      if (k0 < wp) dmma(c0, c1, xa[k0 * Pn], xb[k0 * Pn]);
+      c0 += e0;
+      c1 += e1;
+      const int row = 8 * ib + gid, col = 8 * jb + 2 * tig;
+      if (row >= D || col >= D) continue;
+      c0 *= fact;
+      c1 *= fact;
+      const bool has1 = col + 1 < D;
+      if (corr) {
+        c0 = (c0 == 0.0) ? 0.0 : c0 / (vd[row] * vd[col]);
+        if (has1) c1 = (c1 == 0.0) ? 0.0 : c1 / (vd[row] * vd[col + 1]);
+      }
+      double* dst = o + (long long)row * D + col;
+      if (vec && has1) {
+        *reinterpret_cast<double2*>(dst) = make_double2(c0, c1);
+      } else {
+        dst[0] = c0;
+        if (has1) dst[1] = c1;
+      }
+      if (ib != jb) {  // mirror: 8 consecutive rows -> 64-byte segments
+        o[(long long)col * D + row] = c0;
+        if (has1) o[(long long)(col + 1) * D + row] = c1;
+      }
     }
   }
 }
@@ -207,7 +226,13 @@ extern "C" int fcest_window_cov(const double* y, int N, int D, int window_length
   cudaError_t e = cudaFuncSetAttribute(window_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int nwin = N / step_size;
-  window_cov_kernel<<<N, 256, smem, stream>>>(y, N, D, window_length, step_size, nwin, corr, out);
+  // one resident wave: CTAs per SM limited by shared memory (and 8 x 256 threads), windows dealt round-robin
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const int slots = 148 * per_sm;
+  const int per_cta = (N + slots - 1) / slots;
+  const int grid = (N + per_cta - 1) / per_cta;
+  window_cov_kernel<<<grid, 256, smem, stream>>>(y, N, D, window_length, step_size, nwin, corr, out);
   FCEST_CHECK_LAUNCH();
   return 0;
 }

@@ -81,7 +81,20 @@ class SlidingWindows:
         out = torch.empty((n, d, d), dtype=torch.float64, device=y.device)
         ops.call("fcest_window_cov", ops.ptr(y), n, d, int(window_length), int(step_size),
                  1 if connectivity_metric == 'correlation' else 0, ops.ptr(out))
-        return out.cpu().numpy()
+        return self._to_numpy(out)
+
+    _pinned = None
+
+    @classmethod
+    def _to_numpy(cls, t: torch.Tensor) -> np.ndarray:
+        """Device -> NumPy through a cached pinned staging buffer (a pageable D2H copy of the 8 N D^2
+        byte result would cost more than the estimator itself)."""
+        if cls._pinned is None or cls._pinned.numel() < t.numel():
+            cls._pinned = torch.empty(t.numel(), dtype=torch.float64, pin_memory=True)
+        stage = cls._pinned[:t.numel()].view(t.shape)
+        stage.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return stage.numpy().copy()
 
     def compute_cross_validated_optimal_window_length(
             self,
