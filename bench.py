@@ -255,7 +255,9 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel<128,128,64,32> (3 projection GEMMs per step)",
                          "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three GEMMs,
+                         # from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
+                         "traffic": 759e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 619e6,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/FP64_PEAK.json); "
                                         "MEASURED_PEAKS.json has no fp64 figure",
                          "algorithmic_flops_per_launch": flops["projection"] / 3.0,

@@ -391,20 +391,40 @@ __global__ void sym_matvec_kernel(const double* __restrict__ Tk, long long ldk,
   gs = block_sum(gs, red);
   if (threadIdx.x == 0 && gs_out) gs_out[n] = gs;
   const double* T = Tk + (long long)n * ldk;
-  // row part: acc[i] = sum_{j<=i} T[i,j] p[j]   (one warp per row, coalesced)
+  // single pass over the packed lower triangle, one warp per row i (coalesced): lane j accumulates
+  //   row part    acc_row  += T[i,j] p[j]          (warp-reduced -> out[i])
+  //   column part col[j]   += T[i,j] p[i], j < i   (lane-private registers, columns j = lane + 32 c)
+  constexpr int MAXC = 13;  // M <= 416
+  double col[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) col[c] = 0.0;
+  double* colpart = red + 32;  // nwarps x M per-warp column partials (no atomics: deterministic)
   for (int i = warp; i < M; i += nwarps) {
     const double* Ti = T + (long long)i * (i + 1) / 2;
+    const double pi = p[i];
     double s = 0.0;
-    for (int j = lane; j <= i; j += 32) s += Ti[j] * p[j];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int j = lane + 32 * c;
+      if (j <= i) {
+        const double t = Ti[j];
+        s += t * p[j];
+        if (j < i) col[c] += t * pi;
+      }
+    }
     s = warp_sum(s);
     if (lane == 0) acc[i] = s;
   }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int j = lane + 32 * c;
+    if (j < M) colpart[warp * M + j] = col[c];
+  }
   __syncthreads();
-  // column part: out[j] += sum_{i>j} T[i,j] p[i]   (thread per column, coalesced across threads)
   for (int j = threadIdx.x; j < M; j += blockDim.x) {
-    double s = acc[j];
-    for (int i = j + 1; i < M; ++i) s += T[(long long)i * (i + 1) / 2 + j] * p[i];
-    double v = 2.0 * s;
+    double t = acc[j];
+    for (int w2 = 0; w2 < nwarps; ++w2) t += colpart[w2 * M + j];
+    double v = 2.0 * t;
     if (use_prior) v -= 2.0 * gs * p[j];
     double* dst = dP + (long long)j * lddp + n;
     *dst = accumulate ? (*dst + v) : v;
@@ -467,8 +487,8 @@ extern "C" int fcest_sym_matvec(const double* Tk, long long ldk, const double* P
                                 int use_prior, double* dP, long long lddp, double* gs_out,
                                 int accumulate, cudaStream_t stream) {
   if (N <= 0) return 0;
-  const size_t smem = sizeof(double) * (2 * M + 32);
-  if (smem > 200 * 1024) return FCEST_ERR_UNSUPPORTED;
+  const size_t smem = sizeof(double) * (2 * M + 32 + 8 * M);
+  if (smem > 200 * 1024 || M > 416) return FCEST_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(sym_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   sym_matvec_kernel<<<N, 256, smem, stream>>>(Tk, ldk, P, ldp, M, N, g_var, ldg, R, use_prior, dP,
