@@ -1,0 +1,29 @@
+// Argument block shared by the Wishart likelihood kernels (likelihood.cu: CTA-per-time-step shared-memory /
+// L2-scratch variants; likelihood_warp.cu: warp-per-matrix variant for D <= 55).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fcest {
+
+struct LikParams {
+  const double* fmean; const double* fvar; long long ldf;
+  const double* eps;  // (S, N, R) contiguous
+  const double* y;    // (N, D) contiguous
+  const double* A; int a_mode;  // 0: (D, nu) matrix, 1: (nu,) vector broadcast over rows
+  const double* lam;  // (D,) unconstrained
+  int S, N, D, nu;
+  double* ve;  // (N,)
+  double* g_fmean; double* g_fvar; long long ldg;  // (N, R) or null
+  double* gA_part;    // (N, D*nu) per-time-step partials
+  double* glam_part;  // (N, D)
+  int* info;          // (N,) 0 = ok, else 1-based index of the first non-positive pivot (any sample)
+  int need_grad;
+  double* ws; long long ws_stride;  // BIG variant: per-CTA global scratch for G, T, Yb
+};
+
+// Warp-per-matrix variant.  Returns 0 if launched, a cudaError_t (> 0) on failure, or -1 if the shape
+// is outside what the variant supports (caller falls through to the CTA-per-time-step kernels).
+int launch_loglik_warp(const LikParams& p, cudaStream_t stream);
+bool loglik_warp_supported(int D, int nu);
+
+}  // namespace fcest

@@ -17,28 +17,16 @@
 // Per-CTA partial sums for Abar / lam_bar go to a workspace and are reduced in fixed order
 // (deterministic) by colsum_kernel.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "chol_tiles.cuh"
 #include "common.cuh"
 #include "fcest_b200.h"
+#include "lik_params.cuh"
 
 namespace fcest {
 
-struct LikParams {
-  const double* fmean; const double* fvar; long long ldf;
-  const double* eps;  // (S, N, R) contiguous
-  const double* y;    // (N, D) contiguous
-  const double* A; int a_mode;  // 0: (D, nu) matrix, 1: (nu,) vector broadcast over rows
-  const double* lam;  // (D,) unconstrained
-  int S, N, D, nu;
-  double* ve;  // (N,)
-  double* g_fmean; double* g_fvar; long long ldg;  // (N, R) or null
-  double* gA_part;    // (N, D*nu) per-time-step partials
-  double* glam_part;  // (N, D)
-  int* info;          // (N,) 0 = ok, else 1-based index of the first non-positive pivot (any sample)
-  int need_grad;
-  double* ws; long long ws_stride;  // BIG variant: per-CTA global scratch for G, T, Yb
-};
 
 
 // One CTA (8 warps) per time step; per MC sample a blocked (8x8 tiles) Cholesky / inverse on the fp64
@@ -329,7 +317,16 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   if (p.need_grad && (!g_fvar || !ws_gA_part || !ws_glam_part || !gA || !glam)) return FCEST_ERR_ARGUMENT;
   p.ws = scratch;
   p.ws_stride = 0;
-  if (!bigD) {
+  // D <= 55: warp-per-matrix kernel (likelihood_warp.cu); FCEST_LIK_IMPL=cta forces the CTA-per-time-step one
+  static const bool force_cta = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cta"); }();
+  bool launched = false;
+  if (!force_cta && loglik_warp_supported(D, nu)) {
+    const int rc = launch_loglik_warp(p, stream);
+    if (rc > 0) return rc;
+    launched = (rc == 0);
+  }
+  if (launched) {
+  } else if (!bigD) {
     cudaError_t e = cudaFuncSetAttribute(wishart_loglik_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -1,0 +1,111 @@
+"""Likelihood-only parity: fcest_wishart_loglik (C ABI) against the CPU oracle's closed-form and autograd
+gradients, across the kernel variants (warp-per-matrix D <= 55 with every row-block count, the
+CTA-per-time-step shared-memory kernel, ragged sample counts, vector A modes).
+
+Tolerances: ve 1e-10 relative-to-max (it feeds the 1e-8 ELBO bar), gradients 1e-8 relative-to-max.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wishart_oracle as wo
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _inputs(N, D, S, seed, vector_a=False):
+    rng = np.random.default_rng(seed)
+    R = D * D
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+    fmean = t(0.3 * rng.standard_normal((N, R)))
+    fvar = t(0.05 + rng.random((N, R)))
+    y = t(rng.standard_normal((N, D)))
+    A = t(1.0 + 0.1 * rng.standard_normal(D)) if vector_a else t(np.eye(D) + 0.2 * rng.standard_normal((D, D)))
+    lam = t(wo.inv_softplus(0.01) + 0.3 * rng.standard_normal(D))
+    eps = t(rng.standard_normal((S, N, R)))
+    return fmean, fvar, y, A, lam, eps
+
+
+def _rel(a, b):
+    a = a.detach().cpu().numpy().reshape(-1)
+    b = b.detach().cpu().numpy().reshape(-1)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _check(N, D, S, seed=0, vector_a=False):
+    from fcest_b200 import ops
+    fmean, fvar, y, A, lam, eps = _inputs(N, D, S, seed, vector_a)
+    ve_ref = wo.variational_expectations(fmean, fvar, y, A, lam, eps)
+    mu_bar, v_bar, Abar, lam_bar = wo.likelihood_closed_form_grad(fmean, fvar, y, A, lam, eps)
+    fm_d, fv_d = ops.as_pitched(fmean.cuda()), ops.as_pitched(fvar.cuda())
+    out = ops.wishart_loglik(fm_d, fv_d, eps.cuda(), y.cuda(), A.cuda(), lam.cuda(), need_grad=True)
+    assert int(out["info"].max().item()) == 0
+    assert _rel(out["ve"], ve_ref) < 1e-10, ("ve", D, S)
+    assert _rel(out["g_fmean"], mu_bar) < 1e-8, ("g_fmean", D, S)
+    assert _rel(out["g_fvar"], v_bar) < 1e-8, ("g_fvar", D, S)
+    assert _rel(out["gA"], Abar) < 1e-8, ("gA", D, S)
+    assert _rel(out["glam"], lam_bar) < 1e-8, ("glam", D, S)
+    fwd = ops.wishart_loglik(fm_d, fv_d, eps.cuda(), y.cuda(), A.cuda(), lam.cuda(), need_grad=False)
+    assert _rel(fwd["ve"], ve_ref) < 1e-10
+
+
+# D -> row blocks of the warp kernel: 1..7 -> 1, 8..15 -> 2, ..., 48..55 -> 7; D >= 56 -> CTA kernel
+@pytest.mark.parametrize("D", [1, 2, 3, 7, 8, 9, 15, 16, 23, 24, 31, 32, 39, 40, 47, 48, 50, 55, 56, 64])
+def test_loglik_all_row_block_counts(cuda, D):
+    _check(N=5 if D > 30 else 9, D=D, S=3, seed=D)
+
+
+@pytest.mark.parametrize("S", [1, 2, 5, 8, 9, 13, 16])
+def test_loglik_sample_chunks(cuda, S):
+    """S < 8: fewer warps per CTA; S > 8: several sample chunks accumulated in fixed order."""
+    _check(N=7, D=12, S=S, seed=100 + S)
+    _check(N=3, D=50, S=S, seed=200 + S)
+
+
+@pytest.mark.parametrize("D", [4, 20, 50])
+def test_loglik_vector_A(cuda, D):
+    _check(N=6, D=D, S=4, seed=7, vector_a=True)
+
+
+def test_loglik_many_time_steps(cuda):
+    """More time steps than persistent CTAs: every CTA walks several time steps."""
+    _check(N=700, D=10, S=2, seed=3)
+
+
+def test_loglik_bad_pivot_reported(cuda):
+    from fcest_b200 import ops
+    N, D, S = 4, 20, 2
+    fmean, fvar, y, A, lam, eps = _inputs(N, D, S, 5)
+    lam = torch.full((D,), -800.0, dtype=torch.float64)  # softplus -> 0
+    fmean = torch.zeros_like(fmean)
+    eps = torch.zeros_like(eps)                          # G = 0 -> Sigma = 0: first pivot fails
+    out = ops.wishart_loglik(ops.as_pitched(fmean.cuda()), ops.as_pitched(fvar.cuda()), eps.cuda(), y.cuda(),
+                             A.cuda(), lam.cuda(), need_grad=False)
+    assert (out["info"].cpu().numpy() == 1).all()
+    assert torch.isnan(out["ve"]).all()
+
+
+def test_warp_and_cta_kernels_agree(cuda):
+    """FCEST_LIK_IMPL=cta forces the CTA-per-time-step kernel; both variants must agree to rounding."""
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "from fcest_b200 import ops\n"
+        "import importlib.util as iu; sp = iu.spec_from_file_location('tl', %r); tl = iu.module_from_spec(sp); sp.loader.exec_module(tl); _inputs = tl._inputs\n"
+        "fm, fv, y, A, lam, eps = _inputs(6, 50, 8, 11)\n"
+        "o = ops.wishart_loglik(ops.as_pitched(fm.cuda()), ops.as_pitched(fv.cuda()), eps.cuda(), y.cuda(), A.cuda(), lam.cuda())\n"
+        "np.savez(sys.argv[1], **{k: v.cpu().numpy() for k, v in o.items()})\n" % (ROOT, os.path.abspath(__file__)))
+    outs = []
+    for impl in ("warp", "cta"):
+        path = os.path.join(ROOT, "gpurun_out", f"_lik_{impl}.npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        env = dict(os.environ, FCEST_LIK_IMPL=impl)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=ROOT)
+        outs.append(np.load(path))
+    for k in ("ve", "g_fmean", "g_fvar", "gA", "glam"):
+        a, b = outs[0][k], outs[1][k]
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max(), k
