@@ -55,7 +55,7 @@ __host__ __device__ inline WarpLikLayout wl_layout(int NB, int nu) {
 // Cholesky + inverse of one swizzled 8x8 diagonal tile (rows in lanes, replicated over the four lane
 // groups; registers + shuffles).  On exit the tile holds I = L_bb^-1 (lower, strict upper zeroed) and
 // dinv8[i] = 1 / L_bb[i][i].  Row `yr` (if >= 0) is the bordered y row: its pivot is forced to 1.
-__device__ __forceinline__ int factor_diag_swz(double* tile, double* dinv8, int lane, int yr, int rowbase,
+__device__ __noinline__ int factor_diag_swz(double* tile, double* dinv8, int lane, int yr, int rowbase,
                                                int D, int bad) {
   const int i = lane & 7;
   const bool sw = (i & 2) != 0;
@@ -114,6 +114,13 @@ __device__ __forceinline__ int factor_diag_swz(double* tile, double* dinv8, int 
   return bad;
 }
 
+// L2 prefetch of `bytes` starting at p (128-byte lines dealt to the lanes of one warp)
+__device__ __forceinline__ void prefetch_l2_warp(const void* p, long long bytes, int lane) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (long long off = (long long)lane * 128; off < bytes; off += 32 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+}
+
 #define TI(ib, jb) ((ib) * ((ib) + 1) / 2 + (jb))
 
 template <int NB>
@@ -157,13 +164,27 @@ wishart_loglik_warp_kernel(const LikParams p) {
       const int Sc = min(W, p.S - s0);
       __syncthreads();
       if (ch == 0) {
-        // A. stage am = A o fmean, as = A o sqrt(fvar), y  (shared by all samples of this time step)
-        for (int d = warp; d < D; d += W) {
-          for (int k = lane; k < nu; k += 32) {
-            const int r = d * nu + k;
-            const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + k);
-            am[d * PA + k] = a * fm[r];
-            as_[d * PA + k] = a * sqrt(fv[r]);
+        // A. stage am = A o fmean, as = A o sqrt(fvar), y  (shared by all samples of this time step);
+        //    loads batched four deep so one L2 round trip covers a quarter of the row
+        for (int base = 0; base < R; base += 4 * blockDim.x) {
+          double f4[4], v4[4], a4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = base + u * blockDim.x + tid;
+            if (r < R) {
+              f4[u] = fm[r];
+              v4[u] = fv[r];
+              a4[u] = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = base + u * blockDim.x + tid;
+            if (r < R) {
+              const int d = r / nu, k = r - d * nu;
+              am[d * PA + k] = a4[u] * f4[u];
+              as_[d * PA + k] = a4[u] * sqrt(v4[u]);
+            }
           }
         }
         for (int d = tid; d < Dp; d += blockDim.x) yv[d] = d < D ? p.y[(long long)n * D + d] : 0.0;
@@ -326,6 +347,17 @@ wishart_loglik_warp_kernel(const LikParams p) {
       }
       __syncthreads();
 
+      // next time step of this CTA: pull its noise block (one sample per warp) and its fmean / fvar rows into L2
+      if (ch == nchunk - 1 && n + (int)gridDim.x < N) {
+        const int nn = n + gridDim.x;
+        for (int s2 = warp; s2 < min(W, p.S); s2 += W)
+          prefetch_l2_warp(p.eps + ((long long)s2 * N + nn) * R, (long long)R * 8, lane);
+        if (warp == W - 1) {
+          prefetch_l2_warp(p.fmean + (long long)nn * p.ldf, (long long)R * 8, lane);
+          prefetch_l2_warp(p.fvar + (long long)nn * p.ldf, (long long)R * 8, lane);
+        }
+      }
+
       // ---------------- C. column-block warps: Q'' = Sigma^-1 G - alpha (alpha^T G), sums over samples ------
       if (p.need_grad) {
         double rs[NB];
@@ -337,6 +369,18 @@ wishart_loglik_warp_kernel(const LikParams p) {
           for (int ib = 0; ib < NB; ++ib) U1[ib][0] = U1[ib][1] = U2[ib][0] = U2[ib][1] = 0.0;
           const int colB = 8 * cb + gid;
           const int colC = 8 * cb + 2 * tig;
+          // B-type noise fragments of the first sample; the next sample's are fetched one iteration ahead
+          double en0[NB], en1[NB];
+#define LD_EB(sl_, e0_, e1_)                                                                       \
+  {                                                                                                \
+    const double* ep_ = p.eps + ((long long)(s0 + (sl_)) * N + n) * R;                             \
+    _Pragma("unroll") for (int kb = 0; kb < NB; ++kb) {                                            \
+      const int k_ = 8 * kb + tig;                                                                 \
+      e0_[kb] = (k_ < D && colB < nu) ? __ldg(ep_ + k_ * nu + colB) : 0.0;                         \
+      e1_[kb] = (k_ + 4 < D && colB < nu) ? __ldg(ep_ + (k_ + 4) * nu + colB) : 0.0;               \
+    }                                                                                              \
+  }
+          LD_EB(0, en0, en1);
           for (int sl = 0; sl < Sc; ++sl) {
             const double* Ts = sm + L.off_warp + sl * L.wstride;
             const double* ep = p.eps + ((long long)(s0 + sl) * N + n) * R;
@@ -344,11 +388,10 @@ wishart_loglik_warp_kernel(const LikParams p) {
 #pragma unroll
             for (int kb = 0; kb < NB; ++kb) {
               const int k = 8 * kb + tig;
-              const double e0 = (k < D && colB < nu) ? __ldg(ep + k * nu + colB) : 0.0;
-              const double e1 = (k + 4 < D && colB < nu) ? __ldg(ep + (k + 4) * nu + colB) : 0.0;
-              g0[kb] = am[k * PA + colB] + as_[k * PA + colB] * e0;
-              g1[kb] = am[(k + 4) * PA + colB] + as_[(k + 4) * PA + colB] * e1;
+              g0[kb] = am[k * PA + colB] + as_[k * PA + colB] * en0[kb];
+              g1[kb] = am[(k + 4) * PA + colB] + as_[(k + 4) * PA + colB] * en1[kb];
             }
+            if (sl + 1 < Sc) LD_EB(sl + 1, en0, en1);
 #pragma unroll
             for (int ib = 0; ib < NB; ++ib) {
               const int d = 8 * ib + gid;
@@ -407,23 +450,37 @@ wishart_loglik_warp_kernel(const LikParams p) {
               }
             }
           }
+#undef LD_EB
           // outputs for this column block: mu_bar = a U1, v_bar = a U2 / (2 sd), A_bar part = fm U1 + sd U2
+          // (loads batched first; sd = fv rsqrt(fv), 1 / (2 sd) = rsqrt(fv) / 2)
+          double oa_[NB][2], of_[NB][2], ov_[NB][2];
 #pragma unroll
           for (int ib = 0; ib < NB; ++ib) {
             const int d = 8 * ib + gid;
-            if (d < D) {
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int k = colC + e;
-                if (k < nu) {
-                  const int r = d * nu + k;
-                  const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + k);
-                  const double f = fm[r], sd = sqrt(fv[r]);
-                  const double vm = a * U1[ib][e], vv = a * U2[ib][e] / (2.0 * sd), va = f * U1[ib][e] + sd * U2[ib][e];
-                  const long long o = (long long)n * p.ldg + r, oa = (long long)n * R + r;
-                  if (ch == 0) { p.g_fmean[o] = vm; p.g_fvar[o] = vv; p.gA_part[oa] = va; }
-                  else { p.g_fmean[o] += vm; p.g_fvar[o] += vv; p.gA_part[oa] += va; }
-                }
+            for (int e = 0; e < 2; ++e) {
+              const int k = colC + e;
+              const bool ok = d < D && k < nu;
+              const int r = d * nu + k;
+              oa_[ib][e] = ok ? (p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + k)) : 0.0;
+              of_[ib][e] = ok ? fm[r] : 0.0;
+              ov_[ib][e] = ok ? fv[r] : 1.0;
+            }
+          }
+#pragma unroll
+          for (int ib = 0; ib < NB; ++ib) {
+            const int d = 8 * ib + gid;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int k = colC + e;
+              if (d < D && k < nu) {
+                const int r = d * nu + k;
+                const double rsq = rsqrt(ov_[ib][e]), sd = ov_[ib][e] * rsq;
+                const double vm = oa_[ib][e] * U1[ib][e], vv = oa_[ib][e] * U2[ib][e] * (0.5 * rsq);
+                const double va = of_[ib][e] * U1[ib][e] + sd * U2[ib][e];
+                const long long o = (long long)n * p.ldg + r, oa = (long long)n * R + r;
+                if (ch == 0) { p.g_fmean[o] = vm; p.g_fvar[o] = vv; p.gA_part[oa] = va; }
+                else { p.g_fmean[o] += vm; p.g_fvar[o] += vv; p.gA_part[oa] += va; }
               }
             }
           }

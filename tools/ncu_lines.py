@@ -1,12 +1,13 @@
 """Aggregate ncu per-instruction stall samples by CUDA source line.
 
-usage: python tools/ncu_lines.py <report.ncu-rep> <kernel substring> <cubin file> [top N]
+usage: python tools/ncu_lines.py <report.ncu-rep> <kernel substring> <cubin file> [top N] [mangled substring]
 (ncu's CSV source page is SASS only; the SASS -> line map comes from `nvdisasm -g` on the cubin that
 `cuobjdump -xelf all libfcest_b200.so` extracts -- instruction order is identical.)"""
 import csv, re, subprocess, sys, collections
 
 rep, kname, cubin = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+dname = sys.argv[5] if len(sys.argv) > 5 else kname
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 kern, cur = [], None
@@ -19,7 +20,7 @@ for r in rows:
 k = [k for k in kern if kname in k["name"]][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # locate function
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l][0]
+start = [i for i, l in enumerate(dis) if l.startswith(".text.") and dname in l][0]
 lines, cur_line = [], None
 for l in dis[start + 1:]:
     if l.startswith("//---------------------") or l.startswith(".text."): 
