@@ -23,7 +23,8 @@ struct LikParams {
 
 // Warp-per-matrix variant.  Returns 0 if launched, a cudaError_t (> 0) on failure, or -1 if the shape
 // is outside what the variant supports (caller falls through to the CTA-per-time-step kernels).
-int launch_loglik_warp(const LikParams& p, cudaStream_t stream);
+// *part_rows receives the number of rows of gA_part / glam_part it filled (one per persistent CTA).
+int launch_loglik_warp(const LikParams& p, cudaStream_t stream, int* part_rows);
 bool loglik_warp_supported(int D, int nu);
 
 }  // namespace fcest

@@ -320,8 +320,9 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   // D <= 55: warp-per-matrix kernel (likelihood_warp.cu); FCEST_LIK_IMPL=cta forces the CTA-per-time-step one
   static const bool force_cta = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cta"); }();
   bool launched = false;
+  int part_rows = N;  // rows of the A_bar / lam_bar partial workspaces that the kernel filled
   if (!force_cta && loglik_warp_supported(D, nu)) {
-    const int rc = launch_loglik_warp(p, stream);
+    const int rc = launch_loglik_warp(p, stream, &part_rows);
     if (rc > 0) return rc;
     launched = (rc == 0);
   }
@@ -342,12 +343,12 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
     const int R = D * nu;
     const dim3 cb(32, 32);
     if (a_mode == 0) {
-      colsum_kernel<<<(R + 31) / 32, cb, 0, stream>>>(ws_gA_part, R, N, R, gA, 0);
+      colsum_kernel<<<(R + 31) / 32, cb, 0, stream>>>(ws_gA_part, R, part_rows, R, gA, 0);
     } else {
-      colsum_kernel<<<(nu + 31) / 32, cb, 0, stream>>>(ws_gA_part, R, N, R, gA, nu);
+      colsum_kernel<<<(nu + 31) / 32, cb, 0, stream>>>(ws_gA_part, R, part_rows, R, gA, nu);
     }
     FCEST_CHECK_LAUNCH();
-    colsum_kernel<<<(D + 31) / 32, cb, 0, stream>>>(ws_glam_part, D, N, D, glam, 0);
+    colsum_kernel<<<(D + 31) / 32, cb, 0, stream>>>(ws_glam_part, D, part_rows, D, glam, 0);
     FCEST_CHECK_LAUNCH();
   }
   return 0;

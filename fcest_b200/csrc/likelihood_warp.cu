@@ -153,6 +153,7 @@ wishart_loglik_warp_kernel(const LikParams p) {
   for (int e = tid; e < 2 * Dp * PA; e += blockDim.x) sm[e] = 0.0;  // padding of am / as stays zero
   for (int d = tid; d < Dp; d += blockDim.x) spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
   const int nchunk = (p.S + W - 1) / W;
+  double glam_acc = 0.0;  // thread d < D: this CTA's partial of lam_bar[d] over its time steps (blockDim >= D)
 
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
     const double* fm = p.fmean + (long long)n * p.ldf;
@@ -165,11 +166,12 @@ wishart_loglik_warp_kernel(const LikParams p) {
       __syncthreads();
       if (ch == 0) {
         // A. stage am = A o fmean, as = A o sqrt(fvar), y  (shared by all samples of this time step);
-        //    loads batched four deep so one L2 round trip covers a quarter of the row
-        for (int base = 0; base < R; base += 4 * blockDim.x) {
-          double f4[4], v4[4], a4[4];
+        //    loads batched four deep (the rows were L2-prefetched one time step ahead)
+        constexpr int PF = 4;
+        for (int base = 0; base < R; base += PF * blockDim.x) {
+          double f4[PF], v4[PF], a4[PF];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < PF; ++u) {
             const int r = base + u * blockDim.x + tid;
             if (r < R) {
               f4[u] = fm[r];
@@ -178,7 +180,7 @@ wishart_loglik_warp_kernel(const LikParams p) {
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < PF; ++u) {
             const int r = base + u * blockDim.x + tid;
             if (r < R) {
               const int d = r / nu, k = r - d * nu;
@@ -453,7 +455,10 @@ wishart_loglik_warp_kernel(const LikParams p) {
 #undef LD_EB
           // outputs for this column block: mu_bar = a U1, v_bar = a U2 / (2 sd), A_bar part = fm U1 + sd U2
           // (loads batched first; sd = fv rsqrt(fv), 1 / (2 sd) = rsqrt(fv) / 2)
-          double oa_[NB][2], of_[NB][2], ov_[NB][2];
+          // A_bar partials are accumulated per CTA (row blockIdx.x of the workspace): read-modify-write by the
+          // same lane every time step, so the order of additions is fixed
+          const bool first = (n == (int)blockIdx.x) && ch == 0;
+          double oa_[NB][2], of_[NB][2], ov_[NB][2], og_[NB][2];
 #pragma unroll
           for (int ib = 0; ib < NB; ++ib) {
             const int d = 8 * ib + gid;
@@ -465,6 +470,7 @@ wishart_loglik_warp_kernel(const LikParams p) {
               oa_[ib][e] = ok ? (p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + k)) : 0.0;
               of_[ib][e] = ok ? fm[r] : 0.0;
               ov_[ib][e] = ok ? fv[r] : 1.0;
+              og_[ib][e] = (ok && !first) ? p.gA_part[(long long)blockIdx.x * R + r] : 0.0;
             }
           }
 #pragma unroll
@@ -478,9 +484,10 @@ wishart_loglik_warp_kernel(const LikParams p) {
                 const double rsq = rsqrt(ov_[ib][e]), sd = ov_[ib][e] * rsq;
                 const double vm = oa_[ib][e] * U1[ib][e], vv = oa_[ib][e] * U2[ib][e] * (0.5 * rsq);
                 const double va = of_[ib][e] * U1[ib][e] + sd * U2[ib][e];
-                const long long o = (long long)n * p.ldg + r, oa = (long long)n * R + r;
-                if (ch == 0) { p.g_fmean[o] = vm; p.g_fvar[o] = vv; p.gA_part[oa] = va; }
-                else { p.g_fmean[o] += vm; p.g_fvar[o] += vv; p.gA_part[oa] += va; }
+                const long long o = (long long)n * p.ldg + r;
+                p.gA_part[(long long)blockIdx.x * R + r] = og_[ib][e] + va;
+                if (ch == 0) { p.g_fmean[o] = vm; p.g_fvar[o] = vv; }
+                else { p.g_fmean[o] += vm; p.g_fvar[o] += vv; }
               }
             }
           }
@@ -497,13 +504,12 @@ wishart_loglik_warp_kernel(const LikParams p) {
 
       // ---------------- D. lam_bar, ve, info ----------------
       if (p.need_grad) {
-        for (int d = tid; d < D; d += blockDim.x) {
+        for (int d = tid; d < D; d += blockDim.x) {  // one trip: blockDim >= 32 and the launcher keeps D <= blockDim
           double sa = 0.0, sr = 0.0;
           for (int sl = 0; sl < Sc; ++sl) sa += (sm + L.off_warp + sl * L.wstride + NT * 64 + NB * 64 + Dp)[d];
           for (int w2 = 0; w2 < W; ++w2) sr += (sm + L.off_warp + w2 * L.wstride + NT * 64 + NB * 64 + 2 * Dp)[d];
           const double v = sigmoid_d(p.lam[d]) * wS * (-0.5) * ((double)Sc - sa * yv[d] - sr) / spl[d];
-          const long long o = (long long)n * D + d;
-          if (ch == 0) p.glam_part[o] = v; else p.glam_part[o] += v;
+          glam_acc += v;
         }
       }
       if (tid == 0) {
@@ -520,6 +526,7 @@ wishart_loglik_warp_kernel(const LikParams p) {
       }
     }
   }
+  if (p.need_grad && tid < D) p.glam_part[(long long)blockIdx.x * D + tid] = glam_acc;
 }
 
 #undef TI
@@ -539,7 +546,7 @@ bool loglik_warp_supported(int D, int nu) {
 }
 
 template <int NB>
-static int launch_nb(const LikParams& p, int W, long long smem, cudaStream_t stream) {
+static int launch_nb(const LikParams& p, int W, long long smem, cudaStream_t stream, int* part_rows) {
   auto kern = wishart_loglik_warp_kernel<NB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -552,23 +559,25 @@ static int launch_nb(const LikParams& p, int W, long long smem, cudaStream_t str
   long long grid = (long long)sms * occ;
   if (grid > p.N) grid = p.N;
   kern<<<(int)grid, 32 * W, smem, stream>>>(p);
+  *part_rows = (int)grid;
   return 0;
 }
 
-int launch_loglik_warp(const LikParams& p, cudaStream_t stream) {
+int launch_loglik_warp(const LikParams& p, cudaStream_t stream, int* part_rows) {
   if (!loglik_warp_supported(p.D, p.nu)) return -1;
   const int NB = p.D / 8 + 1;
   int W = p.S < 8 ? p.S : 8;
+  if (p.D > 32 * W) W = (p.D + 31) / 32;  // phase D keeps one lam_bar element per thread
   while (W > 1 && wl_smem_bytes(NB, p.nu, W) > kSmemLimit) --W;
   const long long smem = wl_smem_bytes(NB, p.nu, W);
   switch (NB) {
-    case 1: return launch_nb<1>(p, W, smem, stream);
-    case 2: return launch_nb<2>(p, W, smem, stream);
-    case 3: return launch_nb<3>(p, W, smem, stream);
-    case 4: return launch_nb<4>(p, W, smem, stream);
-    case 5: return launch_nb<5>(p, W, smem, stream);
-    case 6: return launch_nb<6>(p, W, smem, stream);
-    case 7: return launch_nb<7>(p, W, smem, stream);
+    case 1: return launch_nb<1>(p, W, smem, stream, part_rows);
+    case 2: return launch_nb<2>(p, W, smem, stream, part_rows);
+    case 3: return launch_nb<3>(p, W, smem, stream, part_rows);
+    case 4: return launch_nb<4>(p, W, smem, stream, part_rows);
+    case 5: return launch_nb<5>(p, W, smem, stream, part_rows);
+    case 6: return launch_nb<6>(p, W, smem, stream, part_rows);
+    case 7: return launch_nb<7>(p, W, smem, stream, part_rows);
     default: return -1;
   }
 }
