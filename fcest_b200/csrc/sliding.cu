@@ -18,93 +18,207 @@
 
 namespace fcest {
 
-__global__ void __launch_bounds__(256)
-window_cov_kernel(const double* __restrict__ y, int N, int D, int w, int step, int nwin, int corr,
+// Anchored prefix-sum formulation.  A CTA owns a block of G consecutive windows (step 1) and keeps the Gram
+// matrix M_g = sum_{t in window g} u_t u_t^T of the block-centred rows u_t = x_t - c (c = column means of the
+// block's first window) in registers (16 x 16 macro tiles of 2 x 2 DMMA tiles, lower macro tiles only):
+//   window 0 of the block : M_0 accumulated directly over its w rows (two-pass, as np.cov does);
+//   window g > 0          : M_g = M_{g-1} + u_new u_new^T - u_old u_old^T   -- ONE DMMA k-step per tile;
+//   cov_g = (M_g - w d_g d_g^T) / (w - 1),  d_g = window mean of u (exactly the centred second moment).
+// Re-anchoring every G windows bounds the accumulated rounding at ~2 G eps |M|; a guard falls back to the
+// direct accumulation for every window of a block whose windows differ in scale (max_d M_dd) by more than
+// kScaleGuard, which keeps the 1e-12 relative-to-max contract on badly scaled data too.
+constexpr int WC_MAXM = 4;               // macro tiles held per warp
+constexpr double kScaleGuard = 32.0;
+
+__global__ void __launch_bounds__(256, 2)
+window_cov_kernel(const double* __restrict__ y, int N, int D, int w, int step, int nwin, int corr, int G,
                   double* __restrict__ out) {
   extern __shared__ __align__(16) double sm[];
-  const int Dp = (D + 7) / 8 * 8, Pn = pitch4(Dp), wp = (w + 3) / 4 * 4;
-  double* Xs = sm;              // wp x Pn, centred window (zero padded)
-  double* mean = Xs + wp * Pn;  // Dp
-  double* vd = mean + Dp;       // Dp: sqrt(diag(cov))
+  const int Dm = (D + 15) / 16 * 16, Pn = pitch4(Dm);
+  const int RB = w + (G - 1) * step, RBp = (RB + 3) / 4 * 4;
+  double* Xs = sm;                  // RBp x Pn: block rows, centred in place (zero padded rows / columns)
+  double* delta = Xs + RBp * Pn;    // G x Dm: window mean of the centred rows
+  double* isd = delta + G * Dm;     // G x Dm: 1 / sqrt(var) (0 for a constant column)
+  double* red = isd + G * Dm;       // 16: max_d sum_t u^2 per window (scale guard)
+  __shared__ int direct_all;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int pad = w / 2;
   const double fact = 1.0 / (double)(w - 1);
-  const int nb = Dp / 8, ntiles = nb * (nb + 1) / 2;
   const bool vec = ((D & 1) == 0);
-  // persistent over output windows: the grid is sized to one resident wave (see fcest_window_cov)
-  for (int i = blockIdx.x; i < N; i += gridDim.x) {
-    double* o = out + (long long)i * D * D;
-    if (i >= nwin) {  // rows >= int(N / step) stay zero (sliding_windows.py:164-165)
-      for (int e = tid; e < D * D; e += blockDim.x) o[e] = 0.0;
-      continue;
+  // rows >= int(N / step) stay zero (sliding_windows.py:164-165)
+  for (long long e = (long long)nwin * D * D + (long long)blockIdx.x * blockDim.x + tid; e < (long long)N * D * D;
+       e += (long long)gridDim.x * blockDim.x) out[e] = 0.0;
+  const int g0 = blockIdx.x * G;
+  if (g0 >= nwin) return;
+  const int Gc = min(G, nwin - g0);
+  const int start = g0 * step - pad;
+  // stage the block's rows: 16-byte cp.async copies (zero-filled outside the data / past column D) when
+  // rows are 16-byte aligned (D even), all in flight at once
+  if (vec) {
+    const int h = Pn / 2;
+    for (int e = tid; e < RBp * h; e += blockDim.x) {
+      const int t = e / h, d = 2 * (e - t * h);
+      const int src = start + t;
+      const bool live = t < RB && src >= 0 && src < N && d < D;
+      cp_async16(Xs + t * Pn + d, live ? y + (long long)src * D + d : y, live ? 16 : 0);
     }
-    const int start = i * step;
-    __syncthreads();
-    for (int e = tid; e < wp * Pn; e += blockDim.x) {
-      const int t = e / Pn, d = e - t * Pn;
-      double v = 0.0;
-      if (t < w && d < D) {
-        const int src = start + t - pad;
-        if (src >= 0 && src < N) v = y[(long long)src * D + d];
-      }
-      Xs[e] = v;
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
+    for (int t = warp; t < RBp; t += nwarps) {
+      const int src = start + t;
+      const bool live = t < RB && src >= 0 && src < N;
+      const double* yr = y + (long long)(live ? src : 0) * D;
+      for (int d = lane; d < Pn; d += 32) Xs[t * Pn + d] = (live && d < D) ? yr[d] : 0.0;
     }
-    __syncthreads();
-    for (int d = tid; d < Dp; d += blockDim.x) {
-      double s = 0.0;
-      for (int t = 0; t < w; ++t) s += Xs[t * Pn + d];
-      mean[d] = s / w;
+  }
+  if (tid < 16) reinterpret_cast<unsigned long long*>(red)[tid] = 0ull;
+  __syncthreads();
+  // per column: block centre c (mean of the block's first window), centre every row in place
+  for (int d = tid; d < Dm; d += blockDim.x) {
+    double* xc = Xs + d;
+    double s0 = 0.0, s1 = 0.0;
+    int t = 0;
+    for (; t + 1 < w; t += 2) { s0 += xc[t * Pn]; s1 += xc[(t + 1) * Pn]; }
+    if (t < w) s0 += xc[t * Pn];
+    const double c = (d < D) ? (s0 + s1) / w : 0.0;
+    for (t = 0; t < RB; ++t) xc[t * Pn] -= c;
+  }
+  __syncthreads();
+  // per (window, column): two-pass mean offset d_g, variance, scale sum u^2 (-> max over columns per window)
+  for (int e = tid; e < Gc * Dm; e += blockDim.x) {
+    const int g = e / Dm, d = e - g * Dm;
+    const double* xw = Xs + (long long)g * step * Pn + d;
+    double a0 = 0.0, a1 = 0.0;
+    int t = 0;
+    for (; t + 1 < w; t += 2) { a0 += xw[t * Pn]; a1 += xw[(t + 1) * Pn]; }
+    if (t < w) a0 += xw[t * Pn];
+    const double dl = (a0 + a1) / w;
+    double q0 = 0.0, q1 = 0.0, r0 = 0.0, r1 = 0.0;
+    for (t = 0; t + 1 < w; t += 2) {
+      const double ua = xw[t * Pn], ub = xw[(t + 1) * Pn];
+      const double va = ua - dl, vb = ub - dl;
+      q0 += va * va; q1 += vb * vb; r0 += ua * ua; r1 += ub * ub;
     }
-    __syncthreads();
-    for (int e = tid; e < w * Pn; e += blockDim.x) {
-      const int d = e % Pn;
-      if (d < D) Xs[e] -= mean[d];
+    if (t < w) { const double ua = xw[t * Pn], va = ua - dl; q0 += va * va; r0 += ua * ua; }
+    const double var = (q0 + q1) * fact;
+    delta[e] = dl;
+    isd[e] = var > 0.0 ? 1.0 / sqrt(var) : 0.0;
+    // non-negative doubles order like their bit patterns: deterministic max without a reduction tree
+    atomicMax(reinterpret_cast<unsigned long long*>(red) + g, (unsigned long long)__double_as_longlong(r0 + r1));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double lo = INFINITY, hi = 0.0;
+    for (int g = 0; g < Gc; ++g) { const double v = red[g]; lo = fmin(lo, v); hi = fmax(hi, v); }
+    direct_all = (step != 1) || !(hi <= kScaleGuard * lo);
+  }
+  __syncthreads();
+  const bool all_direct = direct_all != 0;
+  const int nbm = Dm / 16, nmac = nbm * (nbm + 1) / 2;
+  const int w4 = w & ~3;
+  // macro tiles in chunks of (warps x WC_MAXM); D <= 112 needs one chunk
+  for (int mbase = 0; mbase < nmac; mbase += nwarps * WC_MAXM) {
+    int Is[WC_MAXM], Js[WC_MAXM];
+    bool on[WC_MAXM];
+#pragma unroll
+    for (int q = 0; q < WC_MAXM; ++q) {
+      const int mt = mbase + warp + q * nwarps;
+      on[q] = mt < nmac;
+      int I = 0, rem = on[q] ? mt : 0;
+      while (rem > I) { rem -= I + 1; ++I; }
+      Is[q] = I; Js[q] = rem;
     }
-    __syncthreads();
-    if (corr) {
-      for (int d = tid; d < Dp; d += blockDim.x) {
-        double s = 0.0;
-        for (int t = 0; t < w; ++t) s += Xs[t * Pn + d] * Xs[t * Pn + d];
-        vd[d] = sqrt(s * fact);
-      }
-      __syncthreads();
-    }
-    // lower tiles only (the Gram matrix is symmetric); each tile is also stored transposed
-    for (int t = warp; t < ntiles; t += nwarps) {
-      int ib = 0, rem = t;
-      while (rem > ib) { rem -= ib + 1; ++ib; }
-      const int jb = rem;
-      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: even / odd k4-steps
-      const double* xa = Xs + tig * Pn + 8 * ib + gid;
-      const double* xb = Xs + tig * Pn + 8 * jb + gid;
-      int k0 = 0;
-      for (; k0 + 4 < wp; k0 += 8) {
-        dmma(c0, c1, xa[k0 * Pn], xb[k0 * Pn]);
-        dmma(e0, e1, xa[(k0 + 4) * Pn], xb[(k0 + 4) * Pn]);
-      }
-      if (k0 < wp) dmma(c0, c1, xa[k0 * Pn], xb[k0 * Pn]);
-      c0 += e0;
-      c1 += e1;
-      const int row = 8 * ib + gid, col = 8 * jb + 2 * tig;
-      if (row >= D || col >= D) continue;
-      c0 *= fact;
-      c1 *= fact;
-      const bool has1 = col + 1 < D;
-      if (corr) {
-        c0 = (c0 == 0.0) ? 0.0 : c0 / (vd[row] * vd[col]);
-        if (has1) c1 = (c1 == 0.0) ? 0.0 : c1 / (vd[row] * vd[col + 1]);
-      }
-      double* dst = o + (long long)row * D + col;
-      if (vec && has1) {
-        *reinterpret_cast<double2*>(dst) = make_double2(c0, c1);
+    double acc[WC_MAXM][2][2][2];
+    for (int g = 0; g < Gc; ++g) {
+      const double* Xw = Xs + (long long)g * step * Pn;
+      if (g == 0 || all_direct) {
+#pragma unroll
+        for (int q = 0; q < WC_MAXM; ++q) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) acc[q][u][v][0] = acc[q][u][v][1] = 0.0;
+          if (!on[q]) continue;
+          const double* pa = Xw + tig * Pn + 16 * Is[q] + gid;
+          const double* pb = Xw + tig * Pn + 16 * Js[q] + gid;
+          for (int k0 = 0; k0 < w4; k0 += 4) {
+            const double a0 = pa[0], a1 = pa[8], b0 = pb[0], b1 = pb[8];
+            dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+            dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+            dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+            dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
+            pa += 4 * Pn;
+            pb += 4 * Pn;
+          }
+          if (w4 < w) {  // ragged last k-step: rows >= w belong to later windows
+            const bool live = w4 + tig < w;
+            const double a0 = live ? pa[0] : 0.0, a1 = live ? pa[8] : 0.0, b0 = live ? pb[0] : 0.0, b1 = live ? pb[8] : 0.0;
+            dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+            dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+            dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+            dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
+          }
+        }
       } else {
-        dst[0] = c0;
-        if (has1) dst[1] = c1;
+        // M_g = M_{g-1} + u_new u_new^T - u_old u_old^T: k-slot 0 = entering row, 1 = leaving row, 2, 3 = 0
+        const double* rnew = Xw + (w - 1) * Pn;   // last row of window g
+        const double* rold = Xw - Pn;             // first row of window g - 1
+        const double* rsel = (tig == 0) ? rnew : rold;
+        const double sgn = (tig == 0) ? 1.0 : -1.0;
+#pragma unroll
+        for (int q = 0; q < WC_MAXM; ++q) {
+          if (!on[q]) continue;
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+          if (tig < 2) {
+            a0 = rsel[16 * Is[q] + gid]; a1 = rsel[16 * Is[q] + 8 + gid];
+            b0 = rsel[16 * Js[q] + gid]; b1 = rsel[16 * Js[q] + 8 + gid];
+            a0 *= sgn; a1 *= sgn;
+          }
+          dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+          dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+          dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+          dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
+        }
       }
-      if (ib != jb) {  // mirror: 8 consecutive rows -> 64-byte segments
-        o[(long long)col * D + row] = c0;
-        if (has1) o[(long long)(col + 1) * D + row] = c1;
+      // epilogue of window g (accumulators stay live for the next window)
+      double* o = out + (long long)(g0 + g) * D * D;
+      const double* dg = delta + g * Dm;
+      const double* ig = isd + g * Dm;
+      const double wd = (double)w;
+#pragma unroll
+      for (int q = 0; q < WC_MAXM; ++q) {
+        if (!on[q]) continue;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int ib = 2 * Is[q] + u, jb = 2 * Js[q] + v;
+            if (jb > ib) continue;  // upper tile of a diagonal macro tile
+            const int row = 8 * ib + gid, col = 8 * jb + 2 * tig;
+            if (row >= D || col >= D) continue;
+            const bool has1 = col + 1 < D;
+            const double dr = dg[row];
+            double c0 = (acc[q][u][v][0] - wd * dr * dg[col]) * fact;
+            double c1 = (acc[q][u][v][1] - wd * dr * dg[col + 1]) * fact;
+            if (corr) {
+              c0 = (c0 == 0.0) ? 0.0 : c0 * (ig[row] * ig[col]);
+              c1 = (c1 == 0.0) ? 0.0 : c1 * (ig[row] * ig[col + 1]);
+            }
+            double* dst = o + (long long)row * D + col;
+            if (vec && has1) {
+              *reinterpret_cast<double2*>(dst) = make_double2(c0, c1);
+            } else {
+              dst[0] = c0;
+              if (has1) dst[1] = c1;
+            }
+            if (ib != jb) {  // mirror: 8 consecutive rows -> 64-byte segments
+              o[(long long)col * D + row] = c0;
+              if (has1) o[(long long)(col + 1) * D + row] = c1;
+            }
+          }
+        }
       }
     }
   }
@@ -220,19 +334,27 @@ extern "C" int fcest_window_cov(const double* y, int N, int D, int window_length
                                 double* out, cudaStream_t stream) {
   if (N <= 0 || D <= 0) return 0;
   if (window_length < 2 || step_size < 1) return FCEST_ERR_ARGUMENT;
-  const int Dp = (D + 7) / 8 * 8, Pn = pitch4(Dp), wp = (window_length + 3) / 4 * 4;
-  const size_t smem = sizeof(double) * ((size_t)wp * Pn + 2 * Dp);
+  const int nwin = N / step_size;
+  const int Dm = (D + 15) / 16 * 16, Pn = pitch4(Dm);
+  // windows per CTA: blocks sized so that two CTAs per SM cover all windows in one resident wave
+  // (step 1 only; larger steps share too few rows for the incremental update to pay)
+  int G = 1;
+  if (step_size == 1) {
+    G = (nwin + 2 * 148 - 1) / (2 * 148);
+    G = G < 2 ? 2 : (G > 16 ? 16 : G);
+  }
+  size_t smem = 0;
+  for (;; --G) {
+    const int RB = window_length + (G - 1) * step_size, RBp = (RB + 3) / 4 * 4;
+    smem = sizeof(double) * ((size_t)RBp * Pn + 2 * (size_t)G * Dm + 16);
+    if (smem <= 110 * 1024 || G == 1) break;
+  }
   if (smem > 227 * 1024) return FCEST_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(window_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int nwin = N / step_size;
-  // one resident wave: CTAs per SM limited by shared memory (and 8 x 256 threads), windows dealt round-robin
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-  const int slots = 148 * per_sm;
-  const int per_cta = (N + slots - 1) / slots;
-  const int grid = (N + per_cta - 1) / per_cta;
-  window_cov_kernel<<<grid, 256, smem, stream>>>(y, N, D, window_length, step_size, nwin, corr, out);
+  int grid = (nwin + G - 1) / G;
+  if (grid < 1) grid = 1;
+  window_cov_kernel<<<grid, 256, smem, stream>>>(y, N, D, window_length, step_size, nwin, corr, G, out);
   FCEST_CHECK_LAUNCH();
   return 0;
 }
