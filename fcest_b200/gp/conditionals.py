@@ -117,9 +117,16 @@ def conditional_forward(kernel, Z, X, q_mu, q_sqrt, vgp: bool, want_kl: bool = T
     return fmean, fvar, kl, state
 
 
-def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: bool = True):
+def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: bool = True,
+                         kl_scale: float = 1.0, gk_reduce=None):
     """Adjoint of ``conditional_forward`` (+ minus the KL gradient): given d ELBO / d (fmean, fvar)
-    returns d ELBO / d {q_mu, q_sqrt, kvar, kls, Z} (constrained kernel parameters)."""
+    returns d ELBO / d {q_mu, q_sqrt, kvar, kls, Z} (constrained kernel parameters).
+
+    Time-sharded evaluation (``fcest_b200.parallel.TimeShardedSVWP``): every rank calls this on its own
+    slice of time points.  ``gk_reduce`` (an in-place SUM all-reduce) is applied to the packed
+    d ELBO / d S_r = g_var^T Pk *before* the per-latent ``tri_grad``, so d q_sqrt comes out complete
+    and identical on every rank (402 MB on the wire at C4 instead of the 800 MB dense gradient);
+    ``kl_scale`` = 1 / world weights the KL part of the *other* gradients, which the caller sums over ranks."""
     dev = g_fmean.device
     M, N = st.P.shape
     R = st.q_mu.shape[1]
@@ -130,6 +137,8 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
     # d/dS (packed) = g_var^T Pk  ->  d q_sqrt
     Gk = torch.empty((R, ldk), dtype=F64, device=dev)
     ops.dgemm(False, False, R, K, N, g_fvar, st.Pk, Gk)
+    if gk_reduce is not None:
+        gk_reduce(Gk)
     dq_sqrt = torch.empty_like(st.q_sqrt)
     ops.call("fcest_tri_grad", ops.ptr(Gk), ldk, ops.ptr(st.q_sqrt), R, M, ops.ptr(dq_sqrt), kl)
     del Gk
@@ -149,10 +158,10 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
     if with_kl:
         flat_q = st.q_mu if st.q_mu.is_contiguous() else None
         if flat_q is not None and dq_mu.is_contiguous():
-            ops.axpby(-1.0, flat_q, 1.0, dq_mu)
+            ops.axpby(-kl_scale, flat_q, 1.0, dq_mu)
         else:  # odd R: pitched views, do it row-block wise through a contiguous temp
             tmp = dq_mu.contiguous()
-            ops.axpby(-1.0, st.q_mu.contiguous(), 1.0, tmp)
+            ops.axpby(-kl_scale, st.q_mu.contiguous(), 1.0, tmp)
             dq_mu = tmp
 
     g_kvar = torch.zeros(1, dtype=F64, device=dev)

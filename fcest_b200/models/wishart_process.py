@@ -118,10 +118,14 @@ class _WishartProcessBase:
     def training_loss(self, data=None):
         return -self.elbo(data)
 
-    def elbo_and_grad(self, data=None, epsilon=None, check: bool = True) -> torch.Tensor:
+    def elbo_and_grad(self, data=None, epsilon=None, check: bool = True, kl_scale: float = 1.0,
+                      gk_reduce=None) -> torch.Tensor:
         """One ELBO evaluation + gradient w.r.t. every trainable variable (the `eval` of the metric).
 
         Gradients (d ELBO / d unconstrained) land in ``Parameter.grad``; returns the ELBO (device scalar).
+        ``kl_scale`` / ``gk_reduce`` are the hooks of the time-sharded multi-GPU evaluation
+        (``fcest_b200.parallel.TimeShardedSVWP``): the KL term is weighted 1 / world on every rank and the
+        packed q_sqrt cotangent is all-reduced inside the backward pass.
         """
         x, y = self._data(data)
         lik = self.likelihood
@@ -129,9 +133,10 @@ class _WishartProcessBase:
         out = lik.variational_expectations(x, fmean, fvar, y, epsilon=epsilon, need_grad=True)
         elbo = torch.empty(1, dtype=F64, device=self.device)
         ops.sum_into(out["ve"], out["ve"].numel(), 1, 1.0, elbo, False)
-        ops.axpby(-1.0, kl, 1.0, elbo)
+        ops.axpby(-float(kl_scale), kl, 1.0, elbo)
         need_Z = self._sparse and self.inducing_variable.Z.trainable
-        g = cond.conditional_backward(st, out["g_fmean"], out["g_fvar"], need_Z=need_Z)
+        g = cond.conditional_backward(st, out["g_fmean"], out["g_fvar"], need_Z=need_Z, kl_scale=float(kl_scale),
+                                      gk_reduce=gk_reduce)
         self.q_mu.grad = g["q_mu"]
         self.q_sqrt.grad = g["q_sqrt"]
         kv, kl_ = self.kernel.variance, self.kernel.lengthscales

@@ -1,9 +1,10 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), independent subjects per rank.
+"""Multi-GPU plumbing: one process per GPU (torchrun).  Two ways the path shards:
 
-The path shards over *subjects* (SURVEY.md 8e (1)): every subject is its own model with its own
-parameters and optimiser state, so there is no data-path collective; ranks only combine the per-step
-ELBO sum (fp64 SUM all-reduce; NCCL over NVLink on GPUs, gloo in the CPU tests).  Kernels always see a
-rank-local slice.
+* independent subjects per rank (``SubjectBatch``) -- no data-path collective, ELBO sum only;
+* one subject, time points sharded over the ranks (``TimeShardedSVWP``): every rank evaluates the
+  likelihood + projection on its slice of the N x S batch and the ELBO and gradients are combined with
+  SUM all-reduces (NCCL over NVLink on GPUs, gloo in the CPU tests).
+Kernels always see a rank-local slice; the collectives are issued from the host between kernel launches.
 """
 from __future__ import annotations
 
@@ -80,3 +81,61 @@ class SubjectBatch:
         if total is None:
             total = torch.zeros(1, dtype=torch.float64, device=device or "cpu")
         return allreduce_sum_(total)
+
+
+def time_partition(num_time_steps: int, world: int, rank: int) -> slice:
+    """Contiguous block of time points owned by ``rank`` (sizes differ by at most one)."""
+    r = subject_partition(num_time_steps, world, rank)
+    return slice(r.start, r.stop)
+
+
+class TimeShardedSVWP:
+    """Data-parallel evaluation of ONE sparse Wishart-process model over the time axis.
+
+    Every rank holds the full parameter set and the full data (x (N,1), y (N,D): < 1 MB); a step evaluates
+    the conditional, the likelihood and their adjoints on this rank's block of time points, then
+      * the packed q_sqrt cotangent Gk = g_var^T Pk (R x M(M+1)/2) is SUM all-reduced inside the backward
+        pass (before the per-latent ``tri_grad``), so ``q_sqrt.grad`` is complete on every rank;
+      * ELBO and the remaining gradients (q_mu, Z, kernel, A, lambda) travel in one flat SUM all-reduce.
+    The KL term carries weight 1 / world on every rank so that the sums count it once.  Results equal the
+    single-GPU evaluation up to the order of the floating-point sums over time points.
+    Only the sparse model shards this way (VGP couples all time points through chol(K(X, X))).
+    """
+
+    def __init__(self, model, world: int | None = None, rank: int | None = None, reduce_=None):
+        if not getattr(model, "_sparse", False):
+            raise NotImplementedError("time sharding needs the sparse (SVWP) model")
+        r, w, _ = dist_env()
+        self.model = model
+        self.world = w if world is None else world
+        self.rank = r if rank is None else rank
+        self.reduce_ = allreduce_sum_ if reduce_ is None else reduce_
+        lik = model.likelihood  # decorrelate the ranks' Monte-Carlo draws (each rank draws its own time block)
+        lik.seed(lik._seed + 7919 * (self.rank + 1))
+
+    def small_grad_parameters(self) -> list:
+        m = self.model
+        ps = [m.q_mu, m.kernel.variance, m.kernel.lengthscales, m.likelihood.A_scale_matrix, m.likelihood.additive_part]
+        if m.inducing_variable.Z.trainable:
+            ps.append(m.inducing_variable.Z)
+        return ps
+
+    def elbo_and_grad(self, data, epsilon=None, check: bool = True) -> torch.Tensor:
+        x, y = data
+        sl = time_partition(len(x), self.world, self.rank)
+        eps = None if epsilon is None else epsilon[:, sl]
+        m = self.model
+        gk_reduce = self.reduce_ if self.world > 1 else None
+        elbo = m.elbo_and_grad((x[sl], y[sl]), epsilon=eps, check=check, kl_scale=1.0 / self.world,
+                               gk_reduce=gk_reduce)
+        if self.world > 1:
+            ps = self.small_grad_parameters()
+            flat = torch.cat([elbo.reshape(1)] + [p.grad.reshape(-1) for p in ps])
+            self.reduce_(flat)
+            elbo = flat[0].clone()
+            o = 1
+            for p in ps:
+                n = p.grad.numel()
+                p.grad = flat[o:o + n].reshape(p.grad.shape).clone()
+                o += n
+        return elbo

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fcest_b200.parallel import SubjectBatch, subject_partition
+from fcest_b200.parallel import SubjectBatch, TimeShardedSVWP, subject_partition, time_partition
 
 
 def test_partition_covers_every_subject_once():
@@ -62,3 +62,77 @@ def test_subject_batch_allreduce_gloo_world2():
     for _, ids, t1, t2, steps in res:
         assert abs(t1 - expected) < 1e-12 and abs(t2 - expected) < 1e-12
         assert steps == [2] * len(ids)
+
+
+def test_time_partition_covers_every_time_step_once():
+    for n in [1, 7, 1200]:
+        for world in [1, 2, 3, 8]:
+            cover = [i for r in range(world) for i in range(n)[time_partition(n, world, r)]]
+            assert cover == list(range(n))
+
+
+class _P:
+    def __init__(self, shape, trainable=True):
+        self.grad = None
+        self.trainable = trainable
+        self.shape = shape
+
+
+class _FakeSparseModel:
+    """Stand-in with the surface TimeShardedSVWP touches; 'ELBO' = sum(y_slice) - kl_scale * 10, gradients are
+    per-slice sums so that the all-reduced values are known in closed form."""
+    _sparse = True
+
+    def __init__(self):
+        ns = type("ns", (), {})
+        self.q_mu, self.q_sqrt = _P((2, 3)), _P((3, 2, 2))
+        self.kernel = ns(); self.kernel.variance, self.kernel.lengthscales = _P(()), _P(())
+        self.likelihood = ns(); self.likelihood.A_scale_matrix, self.likelihood.additive_part = _P((2, 2)), _P((2,))
+        self.likelihood._seed = 0; self.likelihood.seed = lambda s: None
+        self.inducing_variable = ns(); self.inducing_variable.Z = _P((2, 1))
+
+    def elbo_and_grad(self, data, epsilon=None, check=True, kl_scale=1.0, gk_reduce=None):
+        x, y = data
+        t = y.sum()
+        gk = torch.full((3, 3), float(t))
+        if gk_reduce is not None:
+            gk_reduce(gk)
+        self.q_sqrt.grad = gk.clone()
+        for q in [self.q_mu, self.kernel.variance, self.kernel.lengthscales, self.likelihood.A_scale_matrix,
+                  self.likelihood.additive_part, self.inducing_variable.Z]:
+            q.grad = torch.full(q.shape, float(t) - kl_scale, dtype=torch.float64)
+        return t - kl_scale * 10.0
+
+
+def _ts_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    y = torch.arange(14, dtype=torch.float64).reshape(7, 2)
+    x = torch.zeros(7, 1, dtype=torch.float64)
+    m = _FakeSparseModel()
+    sh = TimeShardedSVWP(m)
+    elbo = sh.elbo_and_grad((x, y))
+    out.put((rank, float(elbo), float(m.q_sqrt.grad[0, 0]), float(m.q_mu.grad[0, 0]), float(m.inducing_variable.Z.grad[1, 0])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_time_sharded_allreduce_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ts_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    total = float(sum(range(14)))
+    for _, elbo, gq, gmu, gz in res:
+        assert abs(elbo - (total - 10.0)) < 1e-12      # KL counted once
+        assert abs(gq - total) < 1e-12                 # q_sqrt cotangent reduced inside the backward pass
+        assert abs(gmu - (total - 1.0)) < 1e-12 and abs(gz - (total - 1.0)) < 1e-12
