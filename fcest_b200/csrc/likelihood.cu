@@ -292,10 +292,15 @@ extern "C" long long fcest_wishart_loglik_smem_bytes(int D, int nu) {
 // (0 when the problem fits shared memory and no scratch is needed).
 static const int kBigCtas = 148 * 3;
 extern "C" long long fcest_wishart_loglik_scratch_bytes(int D, int nu) {
-  if (fcest_wishart_loglik_smem_bytes(D, nu) <= 227 * 1024) return 0;
-  const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
-  const long long stride = (long long)Dp * pitch4(Np) + (long long)Dp * pitch4(Dp) + 12LL * Dp;
-  return (long long)sizeof(double) * stride * kBigCtas;
+  long long need = 0;
+  if (!loglik_warp_supported(D, nu) && loglik_tiles_supported(D, nu)) need = loglik_tiles_scratch_bytes(D, nu);
+  if (fcest_wishart_loglik_smem_bytes(D, nu) > 227 * 1024) {
+    const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
+    const long long stride = (long long)Dp * pitch4(Np) + (long long)Dp * pitch4(Dp) + 12LL * Dp;
+    const long long big = (long long)sizeof(double) * stride * kBigCtas;
+    if (big > need) need = big;
+  }
+  return need;
 }
 
 extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, long long ldf,
@@ -317,12 +322,19 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   if (p.need_grad && (!g_fvar || !ws_gA_part || !ws_glam_part || !gA || !glam)) return FCEST_ERR_ARGUMENT;
   p.ws = scratch;
   p.ws_stride = 0;
-  // D <= 55: warp-per-matrix kernel (likelihood_warp.cu); FCEST_LIK_IMPL=cta forces the CTA-per-time-step one
+  // D <= 55: warp-per-matrix kernel (likelihood_warp.cu); FCEST_LIK_IMPL=cta forces the older CTA-per-time-step
+  // kernels of this file (shared memory for D <= ~80, L2 scratch above)
   static const bool force_cta = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cta"); }();
   bool launched = false;
   int part_rows = N;  // rows of the A_bar / lam_bar partial workspaces that the kernel filled
   if (!force_cta && loglik_warp_supported(D, nu)) {
     const int rc = launch_loglik_warp(p, stream, &part_rows);
+    if (rc > 0) return rc;
+    launched = (rc == 0);
+  }
+  // 56 <= D <= 207: shared-memory-tiled CTA-per-matrix kernel (likelihood_tiles.cu)
+  if (!launched && !force_cta && loglik_tiles_supported(D, nu) && scratch != nullptr) {
+    const int rc = launch_loglik_tiles(p, stream, &part_rows);
     if (rc > 0) return rc;
     launched = (rc == 0);
   }

@@ -54,10 +54,23 @@ def _check(N, D, S, seed=0, vector_a=False):
     assert _rel(fwd["ve"], ve_ref) < 1e-10
 
 
-# D -> row blocks of the warp kernel: 1..7 -> 1, 8..15 -> 2, ..., 48..55 -> 7; D >= 56 -> CTA kernel
-@pytest.mark.parametrize("D", [1, 2, 3, 7, 8, 9, 15, 16, 23, 24, 31, 32, 39, 40, 47, 48, 50, 55, 56, 64])
+# D -> row blocks of the warp kernel: 1..7 -> 1, 8..15 -> 2, ..., 48..55 -> 7; D >= 56 -> tiles kernel
+@pytest.mark.parametrize("D", [1, 2, 3, 7, 8, 9, 15, 16, 23, 24, 31, 32, 39, 40, 47, 48, 50, 55])
 def test_loglik_all_row_block_counts(cuda, D):
     _check(N=5 if D > 30 else 9, D=D, S=3, seed=D)
+
+
+# shared-memory-tiled CTA-per-matrix kernel (56 <= D <= 207): every capacity (10, 14, 18, 22, 26 row blocks),
+# D a multiple of 8 (bordered row opens a new block), odd nu (scalar loads); D = 208 falls to the L2-scratch kernel
+@pytest.mark.parametrize("D", [56, 63, 64, 79, 80, 103, 111, 112, 143, 144, 175, 176, 200, 207, 208])
+def test_loglik_tiles_kernel(cuda, D):
+    _check(N=3, D=D, S=2, seed=D)
+
+
+def test_loglik_tiles_many_time_steps_and_samples(cuda):
+    """More time steps than CTAs and several samples: per-CTA A_bar / lam_bar partials, U1 / U2 accumulation."""
+    _check(N=160, D=56, S=3, seed=9)
+    _check(N=4, D=72, S=5, seed=10, vector_a=True)
 
 
 @pytest.mark.parametrize("S", [1, 2, 5, 8, 9, 13, 16])
