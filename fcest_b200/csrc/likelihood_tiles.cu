@@ -63,6 +63,126 @@ __device__ __forceinline__ void cvt_c_to_b(double c0, double c1, int gid, int ti
   b1 = (gid & 1) ? y1 : y0;
 }
 
+
+// Context of one column-block solve (P4); passed by reference through the unrolled step templates.
+struct LtCtx {
+  const double* tiles; const double* am; const double* as_; const double* ep;
+  int D, nu, colC, ycol, gid, tig, oA0, oA1, oT0, oT1;
+};
+
+// G tile (ib, cb) in accumulator layout; column ycol carries e_D
+__device__ __forceinline__ void lt_load_g(const LtCtx& c, int ib, double (&g)[2]) {
+  const int d = 8 * ib + c.gid;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = c.colC + e;
+    double v = 0.0;
+    if (d < c.D && k < c.nu) { const int r = d * c.nu + k; v = c.am[r] + c.as_[r] * __ldg(c.ep + r); }
+    else if (d == c.D && k == c.ycol) v = 1.0;
+    g[e] = v;
+  }
+}
+
+// The loops over tiles are written as template recursion: nvcc stops honouring `#pragma unroll` on the
+// 26 x 26 / 2 nest and would index the accumulator array dynamically (local memory).
+template <int NB, int KB, int IB>
+__device__ __forceinline__ void lt_trail_fwd(double (&acc)[NB][2], const double* tiles, int off, double b) {
+  if constexpr (IB < NB) {
+    dmma(acc[IB][0], acc[IB][1], tiles[TI(IB, KB) * 64 + off], b);
+    lt_trail_fwd<NB, KB, IB + 1>(acc, tiles, off, b);
+  }
+}
+template <int NB, int KB, int IB>
+__device__ __forceinline__ void lt_trail_bwd(double (&acc)[NB][2], const double* tiles, int off, double b) {
+  if constexpr (IB < KB) {
+    dmma(acc[IB][0], acc[IB][1], tiles[TI(KB, IB) * 64 + off], b);
+    lt_trail_bwd<NB, KB, IB + 1>(acc, tiles, off, b);
+  }
+}
+constexpr int LT_PF = 3;  // G tiles in flight ahead of the forward substitution
+// forward, right-looking: H[kb] = I_kb (G[kb] + acc[kb]); acc[ib] -= L[ib][kb] H[kb] (ib > kb)
+template <int NB, int KB>
+__device__ __forceinline__ void lt_fwd(double (&acc)[NB][2], double (&gq)[LT_PF][2], const LtCtx& c) {
+  if constexpr (KB < NB) {
+    double b0, b1;
+    cvt_c_to_b(acc[KB][0] + gq[KB % LT_PF][0], acc[KB][1] + gq[KB % LT_PF][1], c.gid, c.tig, b0, b1);
+    if constexpr (KB + LT_PF < NB) lt_load_g(c, KB + LT_PF, gq[KB % LT_PF]);
+    const double* Ik = c.tiles + TI(KB, KB) * 64;
+    double h0 = 0.0, h1 = 0.0;
+    dmma(h0, h1, Ik[c.oA0], b0);
+    dmma(h0, h1, Ik[c.oA1], b1);
+    acc[KB][0] = h0; acc[KB][1] = h1;
+    cvt_c_to_b(-h0, -h1, c.gid, c.tig, b0, b1);
+    lt_trail_fwd<NB, KB, KB + 1>(acc, c.tiles, c.oA0, b0);
+    lt_trail_fwd<NB, KB, KB + 1>(acc, c.tiles, c.oA1, b1);
+    lt_fwd<NB, KB + 1>(acc, gq, c);
+  }
+}
+// backward, right-looking: Q[kb] = I_kb^T acc[kb]; acc[ib] -= L[kb][ib]^T Q[kb] (ib < kb)
+template <int NB, int KB>
+__device__ __forceinline__ void lt_bwd(double (&acc)[NB][2], const LtCtx& c) {
+  if constexpr (KB >= 0) {
+    double b0, b1;
+    cvt_c_to_b(acc[KB][0], acc[KB][1], c.gid, c.tig, b0, b1);
+    const double* Ik = c.tiles + TI(KB, KB) * 64;
+    double q0 = 0.0, q1 = 0.0;
+    dmma(q0, q1, Ik[c.oT0], b0);
+    dmma(q0, q1, Ik[c.oT1], b1);
+    acc[KB][0] = q0; acc[KB][1] = q1;
+    cvt_c_to_b(-q0, -q1, c.gid, c.tig, b0, b1);
+    lt_trail_bwd<NB, KB, 0>(acc, c.tiles, c.oT0, b0);
+    lt_trail_bwd<NB, KB, 0>(acc, c.tiles, c.oT1, b1);
+    lt_bwd<NB, KB - 1>(acc, c);
+  }
+}
+// epilogue of a column block, two row tiles at a time with every global load issued before the first use:
+// alpha from the e_D column; row sums of Q'' o G; U1 += Gbar, U2 += Gbar o eps (this lane owns its elements)
+template <int NB, int IB>
+__device__ __forceinline__ void lt_epilogue(double (&acc)[NB][2], const LtCtx& c, double* U1, double* U2, double* alpha,
+                                            double* rsw, double wS, bool need_grad, bool first_sample) {
+  if constexpr (IB < NB) {
+    constexpr int T = (IB + 1 < NB) ? 2 : 1;
+    double ee[T][2], gm[T][2], gs[T][2], u1[T][2], u2[T][2];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int d = 8 * (IB + t) + c.gid;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = c.colC + e;
+        const bool ok = need_grad && d < c.D && k < c.nu;
+        const int r = ok ? d * c.nu + k : 0;
+        ee[t][e] = ok ? __ldg(c.ep + r) : 0.0;
+        gm[t][e] = ok ? c.am[r] : 0.0;
+        gs[t][e] = ok ? c.as_[r] : 0.0;
+        u1[t][e] = (ok && !first_sample) ? U1[r] : 0.0;
+        u2[t][e] = (ok && !first_sample) ? U2[r] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int d = 8 * (IB + t) + c.gid;
+      double rs = 0.0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = c.colC + e;
+        const double q = acc[IB + t][e];
+        if (d < c.D && k == c.ycol) alpha[d] = -q;
+        if (need_grad && d < c.D && k < c.nu) {
+          const int r = d * c.nu + k;
+          rs += q * (gm[t][e] + gs[t][e] * ee[t][e]);
+          const double gb = -wS * q;
+          U1[r] = u1[t][e] + gb;
+          U2[r] = u2[t][e] + gb * ee[t][e];
+        }
+      }
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);  // all lanes take part (rows >= D contribute zero)
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      if (c.tig == 0 && d < c.D) rsw[d] += rs;
+    }
+    lt_epilogue<NB, IB + T>(acc, c, U1, U2, alpha, rsw, wS, need_grad, first_sample);
+  }
+}
+
 template <int NB>
 __global__ void __launch_bounds__(LT_WARPS * 32, 1)
 wishart_loglik_tiles_kernel(const LikParams p) {
@@ -117,14 +237,30 @@ wishart_loglik_tiles_kernel(const LikParams p) {
     for (int s = 0; s < p.S; ++s) {
       const double* ep = p.eps + ((long long)s * N + n) * R;
       // ---------------- P1. Sigma tiles = G G^T ----------------
-      auto build_panel = [&](int pi, int buf) {
-        double* dst = pan + buf * Dm * LT_PP;
+      // panel = 8 columns of G; its raw ingredients are loaded into registers before the DMMAs of the current
+      // panel and combined / stored to the other buffer after them (D * 8 / 256 <= 7 elements per thread)
+      constexpr int PE = 7;
+      double pa_[PE], ps_[PE], pe_[PE];
+      auto panel_load = [&](int pi) {
         const int k0 = 8 * pi;
-        for (int e = tid; e < D * 8; e += blockDim.x) {
-          const int d = e >> 3, c = e & 7, k = k0 + c;
-          double v = 0.0;
-          if (k < nu) { const int r = d * nu + k; v = am[r] + as_[r] * __ldg(ep + r); }
-          dst[d * LT_PP + c] = v;
+#pragma unroll
+        for (int i = 0; i < PE; ++i) {
+          const int e = tid + i * LT_WARPS * 32;
+          const int d = e >> 3, k = k0 + (e & 7);
+          const bool ok = d < D && k < nu;
+          const int r = ok ? d * nu + k : 0;
+          pa_[i] = ok ? am[r] : 0.0;
+          ps_[i] = ok ? as_[r] : 0.0;
+          pe_[i] = ok ? __ldg(ep + r) : 0.0;
+        }
+      };
+      auto panel_store = [&](int buf) {
+        double* dst = pan + buf * Dm * LT_PP;
+#pragma unroll
+        for (int i = 0; i < PE; ++i) {
+          const int e = tid + i * LT_WARPS * 32;
+          const int d = e >> 3;
+          if (d < D) dst[d * LT_PP + (e & 7)] = pa_[i] + ps_[i] * pe_[i];
         }
       };
       for (int mbase = 0; mbase < nmac; mbase += LT_WARPS * LT_MQ) {
@@ -146,10 +282,11 @@ wishart_loglik_tiles_kernel(const LikParams p) {
             for (int v = 0; v < 2; ++v) acc[q][u][v][0] = acc[q][u][v][1] = 0.0;
         }
         __syncthreads();  // previous users of the panel buffers are done
-        build_panel(0, 0);
+        panel_load(0);
+        panel_store(0);
         __syncthreads();
         for (int pi = 0; pi < npan; ++pi) {
-          if (pi + 1 < npan) build_panel(pi + 1, (pi + 1) & 1);
+          if (pi + 1 < npan) panel_load(pi + 1);
           const double* P = pan + (pi & 1) * Dm * LT_PP;
 #pragma unroll
           for (int q = 0; q < LT_MQ; ++q) {
@@ -165,6 +302,7 @@ wishart_loglik_tiles_kernel(const LikParams p) {
               dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
             }
           }
+          if (pi + 1 < npan) panel_store((pi + 1) & 1);
           __syncthreads();
         }
         // + diag(softplus(lam)), bordered y row, identity padding; store the lower tiles
@@ -261,97 +399,29 @@ wishart_loglik_tiles_kernel(const LikParams p) {
       // forward only: just the e_D column block (alpha -> quadratic form), on warp 0
       const int cb_first = p.need_grad ? warp : (warp == 0 ? ncb - 1 : ncb);
       for (int cb = cb_first; cb < ncb; cb += LT_WARPS) {
-        const int colC = 8 * cb + 2 * tig;
-        double acc[NB][2];
-        // G tile (ib, cb) in accumulator layout (column ycol = e_D); fetched one step ahead of its use
-#define LT_LOADG(ib_, g_)                                                                 \
-  {                                                                                       \
-    const int d_ = 8 * (ib_) + gid;                                                       \
-    _Pragma("unroll") for (int e = 0; e < 2; ++e) {                                       \
-      const int k_ = colC + e;                                                            \
-      double v_ = 0.0;                                                                    \
-      if (d_ < D && k_ < nu) { const int r_ = d_ * nu + k_; v_ = am[r_] + as_[r_] * __ldg(ep + r_); } \
-      else if (d_ == D && k_ == ycol) v_ = 1.0;                                           \
-      g_[e] = v_;                                                                         \
-    }                                                                                     \
-  }
+        LtCtx c;
+        c.tiles = tiles; c.am = am; c.as_ = as_; c.ep = ep; c.D = D; c.nu = nu; c.colC = 8 * cb + 2 * tig;
+        c.ycol = ycol; c.gid = gid; c.tig = tig; c.oA0 = oA0; c.oA1 = oA1; c.oT0 = oT0; c.oT1 = oT1;
+        double acc[NB][2], gq[LT_PF][2];
 #pragma unroll
         for (int ib = 0; ib < NB; ++ib) acc[ib][0] = acc[ib][1] = 0.0;
-        double gcur[2], gnxt[2];
-        LT_LOADG(0, gcur);
-        // forward, right-looking: H[kb] = I_kb (G[kb] + acc[kb]); acc[ib] -= L[ib][kb] H[kb] (ib > kb)
 #pragma unroll
-        for (int kb = 0; kb < NB; ++kb) {
-          gnxt[0] = gnxt[1] = 0.0;
-          if (kb + 1 < NB) LT_LOADG(kb + 1, gnxt);
-          double b0, b1;
-          cvt_c_to_b(acc[kb][0] + gcur[0], acc[kb][1] + gcur[1], gid, tig, b0, b1);
-          const double* Ik = tiles + TI(kb, kb) * 64;
-          double h0 = 0.0, h1 = 0.0;
-          dmma(h0, h1, Ik[oA0], b0);
-          dmma(h0, h1, Ik[oA1], b1);
-          acc[kb][0] = h0; acc[kb][1] = h1;
-          cvt_c_to_b(-h0, -h1, gid, tig, b0, b1);
-#pragma unroll
-          for (int ib = kb + 1; ib < NB; ++ib) dmma(acc[ib][0], acc[ib][1], tiles[TI(ib, kb) * 64 + oA0], b0);
-#pragma unroll
-          for (int ib = kb + 1; ib < NB; ++ib) dmma(acc[ib][0], acc[ib][1], tiles[TI(ib, kb) * 64 + oA1], b1);
-          gcur[0] = gnxt[0]; gcur[1] = gnxt[1];
+        for (int t = 0; t < LT_PF; ++t) {
+          gq[t][0] = gq[t][1] = 0.0;
+          if (t < NB) lt_load_g(c, t, gq[t]);
         }
-#undef LT_LOADG
+        lt_fwd<NB, 0>(acc, gq, c);
         // row D of H is -alpha^T G: negate it so that the back substitution folds in - alpha (alpha^T G)
         // (the e_D column keeps its sign: its solution is column D of L^-T = (-alpha; 1))
 #pragma unroll
         for (int ib = 0; ib < NB; ++ib) {
           if (ib == yb && gid == yr) {
-            if (colC != ycol) acc[ib][0] = -acc[ib][0];
-            if (colC + 1 != ycol) acc[ib][1] = -acc[ib][1];
+            if (c.colC != ycol) acc[ib][0] = -acc[ib][0];
+            if (c.colC + 1 != ycol) acc[ib][1] = -acc[ib][1];
           }
         }
-        // backward, right-looking: Q[kb] = I_kb^T acc[kb]; acc[ib] -= L[kb][ib]^T Q[kb] (ib < kb)
-#pragma unroll
-        for (int kk = 0; kk < NB; ++kk) {
-          const int kb = NB - 1 - kk;
-          double b0, b1;
-          cvt_c_to_b(acc[kb][0], acc[kb][1], gid, tig, b0, b1);
-          const double* Ik = tiles + TI(kb, kb) * 64;
-          double q0 = 0.0, q1 = 0.0;
-          dmma(q0, q1, Ik[oT0], b0);
-          dmma(q0, q1, Ik[oT1], b1);
-          acc[kb][0] = q0; acc[kb][1] = q1;
-          cvt_c_to_b(-q0, -q1, gid, tig, b0, b1);
-#pragma unroll
-          for (int ib = 0; ib < kb; ++ib) dmma(acc[ib][0], acc[ib][1], tiles[TI(kb, ib) * 64 + oT0], b0);
-#pragma unroll
-          for (int ib = 0; ib < kb; ++ib) dmma(acc[ib][0], acc[ib][1], tiles[TI(kb, ib) * 64 + oT1], b1);
-        }
-        // epilogue: alpha from the e_D column; row sums of Q'' o G; U1 += Gbar, U2 += Gbar o eps
-#pragma unroll
-        for (int ib = 0; ib < NB; ++ib) {
-          {
-            const int d = 8 * ib + gid;
-            double rs = 0.0;
-            if (d < D) {
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int k = colC + e;
-                if (k == ycol) alpha[d] = -acc[ib][e];
-                if (k < nu && p.need_grad) {
-                  const int r = d * nu + k;
-                  const double ee = __ldg(ep + r);
-                  const double g = am[r] + as_[r] * ee;
-                  rs += acc[ib][e] * g;
-                  const double gb = -wS * acc[ib][e];
-                  if (s == 0) { U1[r] = gb; U2[r] = gb * ee; }
-                  else { U1[r] += gb; U2[r] += gb * ee; }
-                }
-              }
-            }
-            rs += __shfl_xor_sync(0xffffffffu, rs, 1);  // all lanes take part (rows >= D contribute zero)
-            rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-            if (tig == 0 && d < D) rsw[d] += rs;
-          }
-        }
+        lt_bwd<NB, NB - 1>(acc, c);
+        lt_epilogue<NB, 0>(acc, c, U1, U2, alpha, rsw, wS, p.need_grad != 0, s == 0);
       }
       __syncthreads();
 
