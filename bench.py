@@ -253,7 +253,7 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_pin.numel() * 8 + y_pin.numel() * 8),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel<128,128,64,32> (3 projection GEMMs per step)",
+            "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel<120,128,40,32,32,3> (3 projection GEMMs per step)",
                          "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three GEMMs,
                          # from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
@@ -265,7 +265,7 @@ def run_cuda(args):
             "roofline_step": {"algorithmic_flops": sum(flops.values()),
                               "achieved": sum(flops.values()) / (t_ms / K * 1e-3) * 1e-12, "peak": peak,
                               "unit": "TFLOP/s", "frac": sum(flops.values()) / (t_ms / K * 1e-3) * 1e-12 / peak},
-            "roofline_likelihood": {"kernel": "wishart_loglik_kernel", "ms": lik_ms,
+            "roofline_likelihood": {"kernel": "wishart_loglik_warp_kernel<7> (+ 2 colsum reductions)", "ms": lik_ms,
                                     "achieved": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12) if lik_ms else None,
                                     "peak": peak, "unit": "TFLOP/s",
                                     "frac": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12 / peak) if lik_ms else None},
