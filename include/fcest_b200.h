@@ -38,8 +38,10 @@ typedef struct CUstream_st* cudaStream_t;
  *   ve : (N,) out, mean over samples of the Gaussian log density
  *   g_fmean, g_fvar : (N, R) pitch ldg, d sum(ve) / d fmean, fvar;  gA : (D,nu) or (nu,);  glam : (D,)
  *   ws_gA_part : (N, R) and ws_glam_part : (N, D) workspaces;  info : (N,)
- *   scratch : fcest_wishart_loglik_scratch_bytes(D, nu) bytes of global memory (0 / NULL while the D x D
- *             problem fits shared memory, D <= ~80; the large-D variant, D <= 400, keeps its tiles there) */
+ *   scratch : fcest_wishart_loglik_scratch_bytes(D, nu) bytes of global memory: 0 / NULL for D <= 55 (warp-per-
+ *             matrix kernel); per-CTA staging slots of the shared-memory-tiled kernel for 56 <= D <= 207; tile
+ *             scratch of the L2-resident fallback for 208 <= D <= 400.
+ *   ws_gA_part / ws_glam_part hold per-CTA (or per-time-step) partial sums that the call reduces in fixed order. */
 long long fcest_wishart_loglik_smem_bytes(int D, int nu);
 long long fcest_wishart_loglik_scratch_bytes(int D, int nu);
 int fcest_wishart_loglik(const double* fmean, const double* fvar, long long ldf, const double* eps,
