@@ -13,7 +13,7 @@ __host__ __device__ __forceinline__ int swz(int r, int c) { return r * 8 + (c ^ 
 // groups; registers + shuffles).  On exit the tile holds I = L_bb^-1 (lower, strict upper zeroed) and
 // dinv8[i] = 1 / L_bb[i][i].  Row `yr` (if >= 0) is the bordered y row: its pivot is forced to 1.
 static __device__ __noinline__ int factor_diag_swz(double* tile, double* dinv8, int lane, int yr, int rowbase,
-                                               int D, int bad) {
+                                               int D, int bad, double* ltile = nullptr) {
   const int i = lane & 7;
   const bool sw = (i & 2) != 0;
   double ph[8];
@@ -54,6 +54,10 @@ static __device__ __noinline__ int factor_diag_swz(double* tile, double* dinv8, 
       const double xk = __shfl_sync(0xffffffffu, x[c], k);
       if (i > k) x[c] -= row[k] * xk;
     }
+  }
+  if (lane < 8 && ltile != nullptr) {  // optional copy of the factor itself (row-major 8 x 8, strict upper zeroed)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ltile[i * 8 + c] = (c <= i) ? row[c] : 0.0;
   }
   if (lane < 8) {
     double out[8];

@@ -465,8 +465,19 @@ extern "C" int fcest_chol_single(double* A, int M, long long lda, int* info, cud
   return 0;
 }
 
+namespace fcest {
+bool chol_inv_tiles_supported(int M);
+int launch_chol_inv_tiles(double* A, int M, long long lda, double* Li, long long ldi, int* info, cudaStream_t stream);
+}
+
 extern "C" int fcest_chol_inv_single(double* A, int M, long long lda, double* Li, long long ldi, int* info,
                                      cudaStream_t stream) {
+  if (chol_inv_tiles_supported(M)) {  // tensor-pipe tile kernel (chol_single_tiles.cu)
+    const int rc = launch_chol_inv_tiles(A, M, lda, Li, ldi, info, stream);
+    if (rc != 0) return rc;
+    FCEST_CHECK_LAUNCH();
+    return 0;
+  }
   if (M > 400) {  // staging buffers no longer fit one CTA's shared memory: unblocked path
     chol_single_kernel<<<1, 1024, 0, stream>>>(A, M, lda, info);
     FCEST_CHECK_LAUNCH();
