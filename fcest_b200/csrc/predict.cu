@@ -8,10 +8,19 @@
 // and streams the samples through shared memory, so nothing of that size ever exists.
 #include <math.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "fcest_b200.h"
 
 namespace fcest {
+
+bool cov_moments_warp_supported(int D, int nu);
+int launch_cov_moments_warp(const double* fmean, const double* fvar, long long ldf, const double* eps, const double* A,
+                            int a_mode, const double* lam, int Sc, int N, int D, int nu, int corr, long long cnt0,
+                            double* mean, double* m2, double* samples, int finalize, double* out_mean,
+                            double* out_std, cudaStream_t stream);
 
 __host__ __device__ inline int pitch4p(int x) {
   int p = (x + 7) / 8 * 8 + 4;
@@ -303,6 +312,14 @@ extern "C" int fcest_cov_moments(const double* fmean, const double* fvar, long l
   p.samples = samples; p.finalize = finalize; p.out_mean = out_mean; p.out_std = out_std;
   if (mean && !m2) return FCEST_ERR_ARGUMENT;
   if (finalize && (!mean || !out_mean || !out_std)) return FCEST_ERR_ARGUMENT;
+  // D <= 56: register-tiled kernel (predict_warp.cu); FCEST_MOM_IMPL=cta forces the shared-memory kernel below
+  static const bool force_cta = [] { const char* v = getenv("FCEST_MOM_IMPL"); return v && !strcmp(v, "cta"); }();
+  if (!force_cta && cov_moments_warp_supported(D, nu)) {
+    const int rc = launch_cov_moments_warp(fmean, fvar, ldf, eps, A, a_mode, lam, Sc, N, D, nu, corr, cnt0, mean, m2,
+                                           samples, finalize, out_mean, out_std, stream);
+    if (rc > 0) return rc;
+    if (rc == 0) { FCEST_CHECK_LAUNCH(); return 0; }
+  }
   if (bigD) {
     const int ctas = N < kMomBigCtas ? N : kMomBigCtas;
     cov_moments_big_kernel<<<ctas, 256, sizeof(double) * 2 * Dp, stream>>>(p, scratch, (long long)Dp * Pg);

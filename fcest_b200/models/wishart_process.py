@@ -175,8 +175,8 @@ class _WishartProcessBase:
         samples = torch.empty((num_mc_samples, n, D, D), dtype=F64, device=dev) if want_samples else None
         nscr = int(_lib.load_library().fcest_cov_moments_scratch_bytes(D, self.nu))
         scratch = torch.empty(nscr // 8, dtype=F64, device=dev) if nscr else None  # large-D tile scratch
-        # stream the samples in chunks that keep the epsilon buffer around 256 MB
-        chunk = num_mc_samples if epsilon is not None else max(1, min(num_mc_samples, (1 << 25) // max(n * R, 1)))
+        # stream the samples in chunks that keep the epsilon buffer around 1 GB
+        chunk = num_mc_samples if epsilon is not None else max(1, min(num_mc_samples, (1 << 27) // max(n * R, 1)))
         done = 0
         while done < num_mc_samples:
             sc = min(chunk, num_mc_samples - done)

@@ -246,3 +246,37 @@ def test_time_sharded_matches_single_gpu(cuda):
         assert abs(elbo - ref_elbo) <= 1e-12 * abs(ref_elbo)
         for q, g in zip(ps, ref):
             assert _rel(q.grad.cpu().numpy().reshape(-1), g.cpu().numpy().reshape(-1)) < 1e-11, q.name
+
+
+@pytest.mark.parametrize("D", [7, 8, 33, 50, 56, 57])
+def test_predict_moments_all_tile_counts(cuda, D):
+    """fcest_cov_moments: register-tiled kernel (D <= 56, every row-block count incl. ragged warps) and the
+    shared-memory kernel just above it, in two chunks (running Welford state) and with raw samples."""
+    from fcest_b200 import ops
+    rng = np.random.default_rng(D)
+    N, S1, S2 = 5, 4, 3
+    R = D * D
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+    fm, fv = t(0.3 * rng.standard_normal((N, R))), t(0.05 + rng.random((N, R)))
+    A, lam = t(np.eye(D) + 0.2 * rng.standard_normal((D, D))), t(wo.inv_softplus(0.01) + 0.3 * rng.standard_normal(D))
+    eps = t(rng.standard_normal((S1 + S2, N, D, D)))
+    for corr, ref_fn in ((0, wo.predict_cov), (1, wo.predict_corr)):
+        m_ref, s_ref = ref_fn(fm, fv, A, lam, eps, D)
+        fm_d, fv_d = ops.as_pitched(fm.cuda()), ops.as_pitched(fv.cuda())
+        mean = torch.empty((N, D, D), dtype=torch.float64, device=cuda)
+        m2 = torch.empty_like(mean); om = torch.empty_like(mean); os_ = torch.empty_like(mean)
+        smp = torch.empty((S1 + S2, N, D, D), dtype=torch.float64, device=cuda)
+        nscr = int(ops._lib.load_library().fcest_cov_moments_scratch_bytes(D, D))
+        scr = torch.empty(max(nscr // 8, 1), dtype=torch.float64, device=cuda)
+        e_d = eps.reshape(S1 + S2, N, R).cuda().contiguous()
+        A_d, lam_d = A.cuda(), lam.cuda()  # keep the device copies alive across the asynchronous launches
+        for (lo, hi, last) in ((0, S1, 0), (S1, S1 + S2, 1)):
+            ops.call("fcest_cov_moments", ops.ptr(fm_d), ops.ptr(fv_d), ops.ld(fm_d), ops.ptr(e_d[lo:hi].contiguous()),
+                     ops.ptr(A_d), 0, ops.ptr(lam_d), hi - lo, N, D, D, corr, lo, ops.ptr(mean), ops.ptr(m2),
+                     ops.ptr(smp[lo:hi]), last, ops.ptr(om), ops.ptr(os_), ops.ptr(scr) if nscr else None)
+        assert np.abs(om.cpu().numpy() - m_ref.numpy()).max() < 1e-9 * max(1.0, float(m_ref.abs().max()))
+        assert np.abs(os_.cpu().numpy() - s_ref.numpy()).max() < 1e-9 * max(1.0, float(s_ref.abs().max()))
+        ref_s = wo.cov_samples(fm, fv, A, lam, eps, D)
+        if corr:
+            ref_s = wo.convert_tensor_to_correlation(ref_s)
+        assert _rel(smp.cpu().numpy(), ref_s.numpy()) < 1e-10
