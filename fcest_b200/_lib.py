@@ -46,6 +46,7 @@ SIGNATURES = {
     "fcest_softplus_fwd": (_i, [_p, _p, _i, _p]),
     "fcest_softplus_bwd": (_i, [_p, _p, _p, _i, _p]),
     "fcest_adam_step": (_i, [_p, _p, _p, _p, _ll, _d, _ll, _d, _d, _d, _d, _p]),
+    "fcest_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _d, _p, _d, _d, _d, _p]),
     "fcest_randn": (_i, [_p, _ll, _ull, _ull, _p]),
     "fcest_cov_moments_scratch_bytes": (_ll, [_i, _i]),
     "fcest_cov_moments": (_i, [_p, _p, _ll, _p, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _p, _p, _p, _i, _p, _p,

@@ -365,9 +365,13 @@ __global__ void softplus_bwd_kernel(const double* u, const double* g_c, double* 
 //   m += (g - m)(1-b1);  v += (g^2 - v)(1-b2);  theta -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps)
 // `sign` = -1 turns an ELBO gradient into a loss gradient.
 // ---------------------------------------------------------------------------------------------
+// alpha_dev != nullptr: the bias-corrected step size is read from device memory (CUDA-graph replays keep the
+// same kernel arguments while the step counter advances)
 __global__ void adam_kernel(double* __restrict__ theta, const double* __restrict__ grad,
                             double* __restrict__ m, double* __restrict__ v, long long n, double sign,
-                            double alpha_t, double b1, double b2, double eps) {
+                            double alpha_t, double b1, double b2, double eps,
+                            const double* __restrict__ alpha_dev = nullptr) {
+  if (alpha_dev != nullptr) alpha_t = alpha_dev[0];
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     const double g = sign * grad[e];
@@ -559,6 +563,16 @@ extern "C" int fcest_adam_step(double* theta, const double* grad, double* m, dou
   const double alpha_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
   adam_kernel<<<grid_for(n, 256), 256, 0, stream>>>(theta, grad, m, v, n, grad_sign, alpha_t, b1, b2,
                                                     eps);
+  FCEST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fcest_adam_step_dev(double* theta, const double* grad, double* m, double* v, long long n,
+                                   double grad_sign, const double* alpha_t, double b1, double b2, double eps,
+                                   cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (alpha_t == nullptr) return FCEST_ERR_ARGUMENT;
+  adam_kernel<<<grid_for(n, 256), 256, 0, stream>>>(theta, grad, m, v, n, grad_sign, 0.0, b1, b2, eps, alpha_t);
   FCEST_CHECK_LAUNCH();
   return 0;
 }

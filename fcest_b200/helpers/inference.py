@@ -34,6 +34,75 @@ class KerasAdam:
             ops.adam_step(p.unconstrained, g.reshape(p.unconstrained.shape), m, v, self.t, grad_sign=-1.0,
                           lr=self.lr, b1=self.b1, b2=self.b2, eps=self.eps)
 
+    # -- CUDA-graph friendly form: the step size lives in a device scalar --------------------------------
+    def advance(self) -> None:
+        """Advance the step counter and refresh the device-resident bias-corrected step size."""
+        self.t += 1
+        alpha_t = self.lr * (1.0 - self.b2 ** self.t) ** 0.5 / (1.0 - self.b1 ** self.t)
+        if getattr(self, "alpha_dev", None) is None:
+            self.alpha_dev = torch.empty(1, dtype=torch.float64, device=self.parameters[0].unconstrained.device)
+        self.alpha_dev.fill_(alpha_t)
+
+    def step_device(self) -> None:
+        """The update of ``step()`` with the step size read from ``alpha_dev`` (call ``advance()`` first)."""
+        for p, m, v in zip(self.parameters, self.m, self.v):
+            g = p.grad
+            if g is None:
+                continue
+            g = g if g.is_contiguous() else g.contiguous()
+            ops.adam_step_dev(p.unconstrained, g.reshape(p.unconstrained.shape), m, v, self.alpha_dev,
+                              grad_sign=-1.0, b1=self.b1, b2=self.b2, eps=self.eps)
+
+
+class GraphedTrainingStep:
+    """One training step (ELBO + gradients + Adam update) captured in a CUDA graph.
+
+    The reference compiles its step with ``tf.function`` (``fcest/helpers/inference.py:111-116``); the analogue
+    here is a captured graph of the ~60 kernel launches of a step, replayed with one launch.  Per step only the
+    Monte-Carlo draw (one Philox launch into a static buffer) and the Adam step size (one fill) are issued
+    outside the graph.  The first call runs eagerly (it is also the warm-up), the second captures, later calls
+    replay.  Cholesky status is checked by ``check()`` (a host sync) instead of every step.
+    """
+
+    def __init__(self, model, data, optimizer: KerasAdam):
+        self.model, self.opt = model, optimizer
+        self.x, self.y = model._data(data)
+        lik = model.likelihood
+        self.eps = torch.empty((lik.num_mc_samples, self.y.shape[0], lik.D * lik.nu), dtype=torch.float64,
+                               device=self.y.device)
+        self.graph = None
+        self.elbo = None
+        self.calls = 0
+
+    def _body(self):
+        elbo = self.model.elbo_and_grad((self.x, self.y), epsilon=self.eps, check=False)
+        self.opt.step_device()
+        return elbo
+
+    def __call__(self) -> torch.Tensor:
+        lik = self.model.likelihood
+        ops.randn(self.eps, lik._seed, lik._draws)
+        lik._draws += 1
+        self.opt.advance()
+        if self.calls == 0:
+            self.elbo = self._body()
+        elif self.calls == 1:
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.elbo = self._body()
+            self.graph.replay()
+        else:
+            self.graph.replay()
+        self.calls += 1
+        return self.elbo
+
+    def check(self) -> None:
+        info = getattr(self.model, "_last_info", None)
+        if info is not None:
+            self.model.likelihood.check_info(info[0])
+            self.model._check_chol(info[1])
+
 
 def run_adam(
     model_type: str,
@@ -69,10 +138,18 @@ def run_adam(
     if log_dir is not None:
         logging.info("TensorBoard monitoring is not available in fcest_b200; ignoring log_dir.")
 
+    import os
+    use_graph = os.environ.get("FCEST_CUDA_GRAPH", "1") != "0" and iterations > 2
+    graphed = GraphedTrainingStep(model, step_data, optimizer) if use_graph else None
     for step in range(iterations):
-        training_loss()          # ELBO + gradients (one fused device pass)
-        optimizer.step()
+        if graphed is not None:
+            graphed()            # ELBO + gradients + Adam update: one CUDA-graph launch
+        else:
+            training_loss()      # ELBO + gradients (one fused device pass)
+            optimizer.step()
         if step % log_interval == 0:
+            if graphed is not None:
+                graphed.check()
             elbo = float(model.elbo(step_data).item())  # a fresh MC draw, as in inference.py:122-125
             logf.append(elbo)
             logging.info(f"Epoch {step:04d}: ELBO (train) {elbo:.2f}")

@@ -146,6 +146,7 @@ class _WishartProcessBase:
             self.inducing_variable.Z.grad = g["Z"]
         lik.A_scale_matrix.grad = out["gA"]
         lik.additive_part.grad = out["glam"]
+        self._last_info = (out["info"], st.info)
         if check:
             lik.check_info(out["info"])
             self._check_chol(st.info)

@@ -135,6 +135,13 @@ def adam_step(theta, grad, m, v, t, grad_sign=-1.0, lr=1e-3, b1=0.9, b2=0.999, e
          float(lr), float(b1), float(b2), float(eps))
 
 
+def adam_step_dev(theta, grad, m, v, alpha_t, grad_sign=-1.0, b1=0.9, b2=0.999, eps=1e-7):
+    """Adam update with the bias-corrected step size in a device scalar (CUDA-graph friendly)."""
+    assert theta.is_contiguous() and grad.is_contiguous() and theta.numel() == grad.numel()
+    call("fcest_adam_step_dev", ptr(theta), ptr(grad), ptr(m), ptr(v), theta.numel(), float(grad_sign), ptr(alpha_t),
+         float(b1), float(b2), float(eps))
+
+
 def wishart_loglik(fmean, fvar, eps, y, A, lam, need_grad=True):
     """Fused likelihood forward (+ backward).  Returns dict(ve, info[, g_fmean, g_fvar, gA, glam])."""
     N, R = fmean.shape

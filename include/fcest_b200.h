@@ -111,6 +111,11 @@ int fcest_softplus_bwd(const double* u, const double* g_c, double* g_u, int n, c
 int fcest_adam_step(double* theta, const double* grad, double* m, double* v, long long n,
                     double grad_sign, long long t, double lr, double b1, double b2, double eps,
                     cudaStream_t stream);
+/*      same update with the bias-corrected step size lr sqrt(1 - b2^t) / (1 - b1^t) read from a DEVICE scalar, so
+ *      that a captured CUDA graph of the training step can be replayed while t advances. */
+int fcest_adam_step_dev(double* theta, const double* grad, double* m, double* v, long long n,
+                        double grad_sign, const double* alpha_t, double b1, double b2, double eps,
+                        cudaStream_t stream);
 
 /* ---- tf.random.normal stand-in (likelihoods.py:130-134, wishart_process.py:200-204,491-495):
  *      Philox4x32-10 + Box-Muller, counter based (element index, offset), keyed by seed. */

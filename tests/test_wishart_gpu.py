@@ -280,3 +280,37 @@ def test_predict_moments_all_tile_counts(cuda, D):
         if corr:
             ref_s = wo.convert_tensor_to_correlation(ref_s)
         assert _rel(smp.cpu().numpy(), ref_s.numpy()) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["svgp", "vgp"])
+def test_cuda_graph_training_step_matches_eager(cuda, kind):
+    """GraphedTrainingStep (eager first call, captured second, replayed afterwards) follows exactly the
+    trajectory of the eager loop `elbo_and_grad + KerasAdam.step` fed with the same Philox draws."""
+    from fcest_b200 import ops
+    from fcest_b200.helpers.inference import GraphedTrainingStep, KerasAdam
+    N, D, S, M = 40, 5, 3, 12
+    steps = 5
+    traj = []
+    for graphed in (False, True):
+        m, x, y, eps, p = _build(kind, N, D, S, M if kind == "svgp" else None)
+        data = (x.numpy(), y.numpy()) if kind == "svgp" else None
+        m.likelihood.seed(77)
+        opt = KerasAdam(m.trainable_parameters)
+        elbos = []
+        if graphed:
+            g = GraphedTrainingStep(m, data, opt)
+            for _ in range(steps):
+                elbos.append(float(g().item()))
+            g.check()
+        else:
+            xd, yd = m._data(data)
+            e = torch.empty((S, yd.shape[0], D * D), dtype=torch.float64, device=cuda)
+            for i in range(steps):
+                ops.randn(e, 77, i)
+                elbos.append(float(m.elbo_and_grad((xd, yd), epsilon=e).item()))
+                opt.step()
+        traj.append((elbos, m.q_mu.unconstrained.cpu().numpy().copy(), m.q_sqrt.unconstrained.cpu().numpy().copy(),
+                     m.kernel.lengthscales.unconstrained.item()))
+    (e0, mu0, sq0, ls0), (e1, mu1, sq1, ls1) = traj
+    assert np.allclose(e0, e1, rtol=1e-13, atol=0.0), (e0, e1)
+    assert _rel(mu1, mu0) < 1e-13 and _rel(sq1, sq0) < 1e-13 and abs(ls1 - ls0) < 1e-14
