@@ -23,8 +23,10 @@ TensorFlow/GPflow path executes for
 PARITY UNPINNED: TensorFlow and GPflow are not installable in the build container (no network) and
 the reference's own tests pin no numeric value on this path, so this
 restatement is checked only against (i) the reference's algebraic identity tests
-(``tests/fcest/models/test_likelihoods.py:54-76``), (ii) finite differences and (iii) an independent
-closed-form gradient derivation.  Noise draws are *injected* (``eps``) instead of drawn from TF's RNG.
+(``tests/fcest/models/test_likelihoods.py:54-76``), (ii) finite differences, (iii) an independent
+closed-form gradient derivation and (iv) independent anchors for the GPflow formulas: scikit-learn's
+Matern(nu=2.5), the un-whitened sparse-GP predictive algebra, the generic Gaussian KL, dense Gaussian algebra
+for the VGP moments and torch.optim.Adam at epsilon = 0 (``tests/test_oracle_cpu.py``).  Noise draws are *injected* (``eps``) instead of drawn from TF's RNG.
 """
 from __future__ import annotations
 

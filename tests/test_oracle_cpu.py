@@ -138,3 +138,93 @@ def test_chunked_oracle_equals_full():
     assert abs(e1 - e2) <= 1e-12 * abs(e1)
     for k in g1:
         assert float((g1[k] - g2[k]).abs().max()) <= 1e-9 * max(float(g1[k].abs().max()), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Independent anchors for the GPflow restatement (the oracle is "parity unpinned": TF / GPflow cannot be
+# installed here).  Each test derives the same quantity by a different route, from third-party code or
+# textbook formulas that do not share the restatement's structure.
+# ------------------------------------------------------------------------------------------------
+def test_matern52_matches_sklearn():
+    """gpflow.kernels.Matern52 restatement == sigma^2 * sklearn Matern(nu=2.5) (independent implementation)."""
+    from sklearn.gaussian_process.kernels import Matern
+    rng = np.random.default_rng(0)
+    X, X2 = rng.random((17, 1)), rng.random((9, 1))
+    var, ls = 1.7, 0.3
+    ref = var * Matern(length_scale=ls, nu=2.5)(X, X2)
+    got = wo.matern52(torch.tensor(X), torch.tensor(X2), torch.tensor(var, dtype=torch.float64),
+                      torch.tensor(ls, dtype=torch.float64)).numpy()
+    assert np.abs(got - ref).max() < 1e-13
+
+
+def test_whitened_conditional_matches_unwhitened_svgp_algebra():
+    """base_conditional(white=True) == the textbook sparse-GP predictive for q(u) = N(m, S) with
+    m = Lm q_mu, S = Lm q_sqrt q_sqrt^T Lm^T:  mean = Kxz Kzz^-1 m,
+    var = kxx - diag(Kxz Kzz^-1 Kzx) + diag(Kxz Kzz^-1 S Kzz^-1 Kzx)   (Hensman et al. 2013, eq. for q(f))."""
+    rng = np.random.default_rng(1)
+    M, N, R = 11, 23, 4
+    Z, X = np.sort(rng.random((M, 1)), 0), rng.random((N, 1))
+    var, ls = 1.3, 0.4
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+    Kzz = wo.matern52(t(Z), t(Z), t(var), t(ls)).numpy() + 1e-6 * np.eye(M)
+    Kzx = wo.matern52(t(Z), t(X), t(var), t(ls)).numpy()
+    q_mu = rng.standard_normal((M, R))
+    q_sqrt = np.tril(rng.standard_normal((R, M, M))) * 0.3 + np.eye(M)[None]
+    fmean, fvar = wo.base_conditional_white(t(Kzx), t(Kzz), t(var * np.ones(N)), t(q_mu), t(q_sqrt))
+    Lm = np.linalg.cholesky(Kzz)
+    KiK = np.linalg.solve(Kzz, Kzx)                       # Kzz^-1 Kzx
+    for r in range(R):
+        m = Lm @ q_mu[:, r]
+        S = Lm @ q_sqrt[r] @ q_sqrt[r].T @ Lm.T
+        mean_ref = KiK.T @ m
+        var_ref = var - np.einsum("mn,mn->n", Kzx, KiK) + np.einsum("mn,mk,kn->n", KiK, S, KiK)
+        assert np.abs(fmean[:, r].numpy() - mean_ref).max() < 1e-9
+        assert np.abs(fvar[:, r].numpy() - var_ref).max() < 1e-9
+
+
+def test_gauss_kl_white_matches_generic_gaussian_kl():
+    """gauss_kl(q_mu, q_sqrt, K=None) == sum_r KL(N(mu_r, L_r L_r^T) || N(0, I)) by the generic formula."""
+    rng = np.random.default_rng(2)
+    M, R = 7, 5
+    q_mu = rng.standard_normal((M, R))
+    q_sqrt = np.tril(rng.standard_normal((R, M, M))) * 0.2 + np.eye(M)[None]
+    got = float(wo.gauss_kl_white(torch.tensor(q_mu), torch.tensor(q_sqrt)))
+    ref = 0.0
+    for r in range(R):
+        S = q_sqrt[r] @ q_sqrt[r].T
+        ref += 0.5 * (np.trace(S) + q_mu[:, r] @ q_mu[:, r] - M - np.linalg.slogdet(S)[1])
+    assert abs(got - ref) < 1e-11 * max(1.0, abs(ref))
+
+
+def test_vgp_moments_match_dense_gaussian_algebra():
+    """VGP.elbo moments: f = L v with v ~ N(q_mu, q_sqrt q_sqrt^T)  =>  mean = L q_mu, var = diag(L S L^T)."""
+    rng = np.random.default_rng(3)
+    N, R = 9, 3
+    x = np.sort(rng.random((N, 1)), 0)
+    p = {"u_var": torch.tensor(wo.inv_softplus(1.2), dtype=torch.float64),
+         "u_ls": torch.tensor(wo.inv_softplus(0.35), dtype=torch.float64),
+         "q_mu": torch.tensor(rng.standard_normal((N, R))),
+         "q_sqrt": torch.tensor(np.tril(rng.standard_normal((R, N, N))) * 0.3 + np.eye(N)[None])}
+    fmean, fvar = wo.vgp_fmean_fvar(torch.tensor(x), p)
+    K = wo.matern52(torch.tensor(x), torch.tensor(x), torch.tensor(1.2, dtype=torch.float64),
+                    torch.tensor(0.35, dtype=torch.float64)).numpy() + 1e-6 * np.eye(N)
+    L = np.linalg.cholesky(K)
+    for r in range(R):
+        S = p["q_sqrt"][r].numpy() @ p["q_sqrt"][r].numpy().T
+        assert np.abs(fmean[:, r].numpy() - L @ p["q_mu"][:, r].numpy()).max() < 1e-12
+        assert np.abs(fvar[:, r].numpy() - np.diag(L @ S @ L.T)).max() < 1e-12
+
+
+def test_keras_adam_equals_torch_adam_at_zero_epsilon():
+    """With epsilon = 0 the Keras form (bias correction folded into the step size) and torch.optim.Adam coincide."""
+    g = torch.Generator().manual_seed(0)
+    theta0 = torch.randn(50, dtype=torch.float64, generator=g)
+    w = torch.nn.Parameter(theta0.clone())
+    opt = torch.optim.Adam([w], lr=1e-3, betas=(0.9, 0.999), eps=0.0)
+    theta, m, v = theta0.clone(), torch.zeros(50, dtype=torch.float64), torch.zeros(50, dtype=torch.float64)
+    for t in range(1, 6):
+        grad = torch.randn(50, dtype=torch.float64, generator=g)
+        w.grad = grad.clone()
+        opt.step()
+        theta, m, v = wo.keras_adam_step(theta, grad, m, v, t, eps=0.0)
+        assert (theta - w.detach()).abs().max() < 1e-15
