@@ -11,6 +11,8 @@
 // Each window is computed directly (two-pass), NOT by differencing prefix sums: the reference's
 // 1e-12 tolerance does not survive a global prefix-sum on non-centred data.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "chol_tiles.cuh"
 #include "common.cuh"
@@ -326,6 +328,17 @@ window_cv_kernel(const double* __restrict__ y, int N, int D, int w_min, int w_st
   }
 }
 
+// table[:, wi] = -inf for the rank-deficient window lengths wi < wi0 (w - 2 < D)
+__global__ void window_cv_fill_singular_kernel(double* __restrict__ table, long long ldt, int num_t, int wi0) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)num_t * wi0;
+       e += (long long)gridDim.x * blockDim.x)
+    table[(e / wi0) * ldt + (e % wi0)] = -INFINITY;
+}
+
+bool window_cv_tiles_supported(int D);
+int launch_window_cv_tiles(const double* y, int N, int D, int w_min, int w_step, int wi0, int num_w, int t_min,
+                           int t_step, int num_t, double rel_tol, double* table, long long ldt, cudaStream_t stream);
+
 }  // namespace fcest
 
 using namespace fcest;
@@ -366,6 +379,23 @@ extern "C" int fcest_window_cv(const double* y, int N, int D, int w_min, int w_s
   const int w_max = w_min + (num_w - 1) * w_step;
   if (w_min < 3 || t_min - w_max / 2 < 0 || t_min + (num_t - 1) * t_step + (w_max + 1) / 2 > N)
     return FCEST_ERR_ARGUMENT;
+  static const bool force_cta = [] { const char* v = getenv("FCEST_CV_IMPL"); return v && !strcmp(v, "cta"); }();
+  if (!force_cta && window_cv_tiles_supported(D) && w_step >= 1) {
+    // tile kernel (sliding_cv_tiles.cu): window lengths with w - 2 < D are rank deficient -> -inf, no work
+    int wi0 = 0;
+    while (wi0 < num_w && (w_min + wi0 * w_step) - 2 < D) ++wi0;
+    if (wi0 > 0) {
+      window_cv_fill_singular_kernel<<<148, 256, 0, stream>>>(table, ldt, num_t, wi0);
+      FCEST_CHECK_LAUNCH();
+    }
+    if (wi0 < num_w) {
+      const int rc = launch_window_cv_tiles(y, N, D, w_min, w_step, wi0, num_w, t_min, t_step, num_t, rel_tol, table, ldt,
+                                            stream);
+      if (rc != 0) return rc;
+      FCEST_CHECK_LAUNCH();
+    }
+    return 0;
+  }
   const int Dp = (D + 7) / 8 * 8, Pd = pitch4(Dp);
   const size_t smem = sizeof(double) * ((size_t)Dp * Pd + 12 * (size_t)Dp + 8 * 96 + 2 * Dp + 8);
   if (smem > 227 * 1024) return FCEST_ERR_UNSUPPORTED;
