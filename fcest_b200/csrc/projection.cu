@@ -249,23 +249,27 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
         cp_async16(Wc + i * TRI_PITCH + c2, bytes > 0 ? L + (long long)i * M + k : L, bytes);
       }
     } else {
-      for (int e = tid; e < M * TRI_KP; e += blockDim.x) {
-        const int i = e / TRI_KP, kk = e - i * TRI_KP, k = k0 + kk;
-        double* dst = Wc + i * TRI_PITCH + kk;
-        if (k < M) {
-          const int idx = (k <= i) ? i * (i + 1) / 2 + k : k * (k + 1) / 2 + i;
-          cp_async8(dst, G + idx);
-        } else {
-          *dst = 0.0;
+      if (lane < TRI_KP) {  // one warp per slab row, lanes over the panel's 24 columns
+        const int kk = lane, k = k0 + kk;
+        for (int i = warp; i < M; i += TRI_WARPS) {
+          double* dst = Wc + i * TRI_PITCH + kk;
+          if (k < M) {
+            const int idx = (k <= i) ? i * (i + 1) / 2 + k : k * (k + 1) / 2 + i;
+            cp_async8(dst, G + idx);
+          } else {
+            *dst = 0.0;
+          }
         }
       }
       double* Lr = Wc + Mp * TRI_PITCH;                    // TRI_KP x PL: row panel of L (cols <= row)
       const int rows = min(TRI_KP, M - k0);
-      for (int e = tid; e < rows * (Mp / 2); e += blockDim.x) {
-        const int kk = e / (Mp / 2), j = 2 * (e % (Mp / 2)), k = k0 + kk;
-        int bytes = (min(M, k + 1) - j) * 8;                // only columns j <= k (and < M) are non-zero
-        bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
-        cp_async16(Lr + kk * PL + j, bytes > 0 ? L + (long long)k * M + j : L, bytes);
+      for (int kk = warp; kk < rows; kk += TRI_WARPS) {       // one warp per row of the L panel
+        const int k = k0 + kk;
+        for (int j = 2 * lane; j < Mp; j += 64) {
+          int bytes = (min(M, k + 1) - j) * 8;              // only columns j <= k (and < M) are non-zero
+          bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+          cp_async16(Lr + kk * PL + j, bytes > 0 ? L + (long long)k * M + j : L, bytes);
+        }
       }
       for (int e = tid; e < (TRI_KP - rows) * Mp; e += blockDim.x)
         Lr[(rows + e / Mp) * PL + e % Mp] = 0.0;
@@ -274,9 +278,18 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
   };
   // strict-upper entries of the slab's diagonal square must read as zero (L lower triangular)
   auto mask_diag = [&](int pnl, int buf) {
-    if (GRAD) return;                                       // grad: Lr is masked by the copy sizes above
     double* Wc = sm + buf * stage_doubles;
     const int k0 = pnl * TRI_KP;
+    if (GRAD) {
+      // grad: Lr is masked by the copy sizes above.  out = (Gs + diag(Gk_ii) - kl I) L: the packed diagonal holds
+      // W_ii (not 2 W_ii) and the KL term is -kl L, so the slab's diagonal becomes 2 Gk_ii - kl and the epilogue
+      // needs no L / G reloads
+      if (tid < TRI_KP && k0 + tid < M) {
+        double* d = Wc + (k0 + tid) * TRI_PITCH + tid;
+        *d = 2.0 * *d - kl;
+      }
+      return;
+    }
     for (int e = tid; e < TRI_KP * TRI_KP; e += blockDim.x) {
       const int ii = e / TRI_KP, kk = e - ii * TRI_KP;
       if (kk > ii && k0 + ii < Mp) Wc[(k0 + ii) * TRI_PITCH + kk] = 0.0;
@@ -290,7 +303,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
     cp_async_wait<1>();
     __syncthreads();
     mask_diag(pnl, buf);
-    if (!GRAD) __syncthreads();
+    __syncthreads();
     const double* Wc = sm + buf * stage_doubles;
     const double* Lr = Wc + Mp * TRI_PITCH;
     const int kb_lo = 3 * pnl, kb_hi = min(nb, 3 * pnl + 3) - 1;   // blocks of this panel (inclusive)
@@ -343,9 +356,8 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
           out_packed[(long long)r * ldk + (long long)row * (row + 1) / 2 + col] = c;
           if (col == row) tr += c;
         } else {
-          const double l = L[(long long)row * M + col];
-          double v = c + G[(long long)row * (row + 1) / 2 + row] * l - kl * l;
-          if (col == row) v += kl / l;
+          double v = c;
+          if (col == row) v += kl / L[(long long)row * M + row];
           dq_sqrt[(long long)r * M * M + (long long)row * M + col] = v;
         }
       }
