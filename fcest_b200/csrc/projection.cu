@@ -232,6 +232,8 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
     acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0;
   }
 
+  // syrk: the diagonal of L (KL piece sum log L_mm^2) is fetched now so its latency hides under the panel loop
+  const double diag_l = (!GRAD && tid < M) ? L[(long long)tid * M + tid] : 1.0;
   // zero both stages once: rows >= M (padding) are never written by the loaders
   for (int e = tid; e < 2 * stage_doubles; e += blockDim.x) sm[e] = 0.0;
   __syncthreads();
@@ -367,8 +369,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
     __shared__ double red[32];
     const long long K = (long long)M * (M + 1) / 2;
     for (long long idx = K + tid; idx < ldk; idx += blockDim.x) out_packed[(long long)r * ldk + idx] = 0.0;
-    double ld = 0.0;
-    for (int m = tid; m < M; m += blockDim.x) { const double d = L[(long long)m * M + m]; ld += log(d * d); }
+    double ld = (tid < M) ? log(diag_l * diag_l) : 0.0;  // diag_l was fetched at kernel start (M <= 200 < blockDim)
     tr = block_sum(tr, red);
     ld = block_sum(ld, red);
     if (tid == 0) { klp[2 * r] = tr; klp[2 * r + 1] = ld; }
