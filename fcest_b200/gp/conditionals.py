@@ -30,6 +30,10 @@ def _round_up(x: int, m: int) -> int:
 
 _side_streams: dict = {}
 
+# The two independent backward chains (d q_sqrt: GEMM + tri_grad; d P: GEMM + sym_matvec + single-matrix chain) run
+# on two streams.  bench.py switches this off for its per-kernel roofline pass, where every launch is timed alone.
+OVERLAP_BACKWARD = True
+
 
 def _side_stream(dev) -> torch.cuda.Stream:
     """One auxiliary stream per device: the latency-bound single-matrix chain (kernel matrix ->
@@ -134,13 +138,22 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
     ldk = st.Pk.shape[1]
     kl = 1.0 if with_kl else 0.0
 
-    # d/dS (packed) = g_var^T Pk  ->  d q_sqrt
+    # d/dS (packed) = g_var^T Pk  ->  d q_sqrt.  This chain (GEMM, optional all-reduce, tri_grad) is independent of
+    # the d P chain below: it runs on the auxiliary stream so that the partial last waves of the two large GEMMs
+    # and the latency-bound single-matrix kernels at the end of the d P chain overlap with it.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
     Gk = torch.empty((R, ldk), dtype=F64, device=dev)
-    ops.dgemm(False, False, R, K, N, g_fvar, st.Pk, Gk)
-    if gk_reduce is not None:
-        gk_reduce(Gk)
     dq_sqrt = torch.empty_like(st.q_sqrt)
-    ops.call("fcest_tri_grad", ops.ptr(Gk), ldk, ops.ptr(st.q_sqrt), R, M, ops.ptr(dq_sqrt), kl)
+    chain_stream = side if OVERLAP_BACKWARD else main
+    if OVERLAP_BACKWARD:
+        side.wait_stream(main)
+    with torch.cuda.stream(chain_stream):
+        ops.dgemm(False, False, R, K, N, g_fvar, st.Pk, Gk)
+        if gk_reduce is not None:
+            gk_reduce(Gk)
+        ops.call("fcest_tri_grad", ops.ptr(Gk), ldk, ops.ptr(st.q_sqrt), R, M, ops.ptr(dq_sqrt), kl)
+    Gk.record_stream(chain_stream)
     del Gk
 
     # T_n (packed) = g_var Sk  ->  dP = 2 T_n p_n (- prior term)
@@ -201,4 +214,6 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
         ops.matern52_bwd(st.Z, st.Z, st.kvar, st.kls, X5, True, g_kvar, g_kls, None, True)
         if not st.vgp:
             ops.matern52_bwd(st.Z, st.X, st.kvar, st.kls, dKmn, False, g_kvar, g_kls, None, True)
+    if OVERLAP_BACKWARD:
+        main.wait_stream(side)
     return {"q_mu": dq_mu[:, :R], "q_sqrt": dq_sqrt, "kvar": g_kvar, "kls": g_kls, "Z": gZ}
