@@ -13,8 +13,7 @@ def _mk(rows, cols, dev, g):
 
 
 @pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, True), (False, False)])
-# the last two shapes have >= 4 x 148 output tiles and no split-K: the persistent kernel with the dynamic tile
-# counter (ragged edge tiles, K not a multiple of the k-tile, several launches in a row on rotating slots)
+# the last two shapes have thousands of output tiles and no split-K (ragged edge tiles, K not a multiple of the k-tile)
 @pytest.mark.parametrize("M,N,K", [(7, 9, 5), (64, 64, 16), (130, 257, 100), (200, 1200, 200), (1200, 225, 1035),
                                     (300, 400, 3000), (2500, 4100, 100), (1234, 10001, 333)])
 def test_dgemm_layouts(cuda, a_k, b_k, M, N, K):
