@@ -142,6 +142,9 @@ int fcest_batched_chol_info(const double* A, int B, int D, double atol, int* inf
  *      (fcest/models/sliding_windows.py:109-174; np.cov per zero-padded window, optional cov -> corr of
  *      fcest/helpers/array_operations.py:37-53) and find_cross_validated_optimal_window_length (:199-274).
  *   window_cov : y (N,D) -> out (N,D,D); out[i] = cov(padded rows [i*step, i*step + w)), i < N/step, else 0.
+ *                (step 1: blocks of consecutive windows per CTA, the centred Gram matrix moved from window to window
+ *                by a rank-2 update and re-anchored by a direct two-pass accumulation at every block start; a scale
+ *                guard falls back to the direct accumulation, so results hold to 1e-12 relative-to-max.)
  *   window_cv  : table[ti*ldt + wi] = logpdf(y_t; 0, cov(window of length w around t without its centre row)),
  *                w = w_min + wi*w_step, t = t_min + ti*t_step; -inf when the window covariance is singular
  *                (w - 2 < D, or a Cholesky pivot below rel_tol * max diagonal). */
