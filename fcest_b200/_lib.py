@@ -54,6 +54,8 @@ SIGNATURES = {
     "fcest_batched_chol_info": (_i, [_p, _i, _i, _d, _p, _p, _p]),
     "fcest_window_cov": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "fcest_window_cv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _d, _p, _ll, _p]),
+    "fcest_filtfilt_scratch_bytes": (_ll, [_i, _ll, _i]),
+    "fcest_filtfilt": (_i, [_p, _i, _ll, _p, _p, _p, _i, _p, _p, _p]),
     "fcest_launch_count": (_ll, []),
     "fcest_launch_count_add": (_ll, [_ll]),
 }

@@ -3,9 +3,10 @@
 Same class, constructor and method names / defaults as the reference
 (``fcest/models/sliding_windows.py:27-427``).  ``overlapping_windowed_cov_estimation`` and the
 cross-validated window search run in ``fcest_window_cov`` / ``fcest_window_cv``; inputs and outputs stay
-NumPy / pandas as in the reference.  Out of scope here: the optional Butterworth
-high-pass filter that the reference applies when ``repetition_time`` is passed to
-``overlapping_windowed_cov_estimation``, and CSV save / load.
+NumPy / pandas as in the reference.  The optional Butterworth high-pass filter the reference applies when
+``repetition_time`` is passed to ``overlapping_windowed_cov_estimation`` runs on the device too
+(``fcest_filtfilt``, ``helpers/filtering.py``), so the data makes one trip to HBM.  Out of scope here
+(SURVEY.md 2.1 row 8): CSV save / load.
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ import pandas as pd
 import torch
 
 from .. import ops
+from ..helpers.filtering import highpass_filter_data
 
 # scipy.stats._multivariate._eigvalsh_to_eps: 1e6 * eps relative eigenvalue threshold for "singular"
 _SINGULAR_REL_TOL = 1e6 * float(np.finfo(np.float64).eps)
@@ -72,12 +74,11 @@ class SlidingWindows:
             connectivity_metric: str = 'covariance',
     ) -> np.array:
         """Overlapping sliding-windows estimate, (N, D, D) -- sliding_windows.py:109-174."""
-        if repetition_time is not None:
-            raise NotImplementedError(
-                "High-pass filtering before windowing (reference filtering.py:12-93) is outside the B200 hot "
-                "path; filter the data first and call with repetition_time=None.")
         n, d = self.num_time_steps, self.num_time_series
         y = self._y_device()
+        # Highpass filtering as recommended by Leonardi2015 (sliding_windows.py:147-154).
+        if repetition_time is not None:
+            y = highpass_filter_data(y, window_length=window_length, repetition_time=repetition_time)
         out = torch.empty((n, d, d), dtype=torch.float64, device=y.device)
         ops.call("fcest_window_cov", ops.ptr(y), n, d, int(window_length), int(step_size),
                  1 if connectivity_metric == 'correlation' else 0, ops.ptr(out))

@@ -154,6 +154,19 @@ int fcest_window_cv(const double* y, int N, int D, int w_min, int w_step, int nu
                     int t_step, int num_t, double rel_tol, double* table, long long ldt,
                     cudaStream_t stream);
 
+/* ---- zero-phase high-pass filtering in front of the sliding-window estimator
+ *      (fcest/helpers/filtering.py:12-67 -> scipy.signal.filtfilt(b, a, column), defaults padtype 'odd',
+ *      padlen = 3 * (order + 1), method 'pad'; called from fcest/models/sliding_windows.py:147-154).
+ *   x, out : (N, C) device arrays, every column filtered independently (C = D, or subjects * D);
+ *   b, a   : HOST arrays of order + 1 transfer-function coefficients, a[0] == 1 (copied into the launch
+ *            parameters); zi : HOST array of `order` steady-state initial conditions (scipy lfilter_zi);
+ *   scratch: fcest_filtfilt_scratch_bytes(N, C, order) device bytes (the forward pass over the extended signal).
+ *   Products and sums are rounded separately in scipy's order, so results are bit-identical to scipy's.
+ *   Returns -2 when N <= padlen (scipy raises ValueError there), -3 for order > 8 or a[0] != 1. */
+long long fcest_filtfilt_scratch_bytes(int N, long long C, int order);
+int fcest_filtfilt(const double* x, int N, long long C, const double* b, const double* a, const double* zi,
+                   int order, double* scratch, double* out, cudaStream_t stream);
+
 /* ---- instrumentation: number of kernels this library has launched since load (bench.py "gpu_launches"). */
 long long fcest_launch_count(void);
 long long fcest_launch_count_add(long long n);

@@ -4,6 +4,8 @@
 
 * sliding_*.npz -- outputs of the REFERENCE's own SlidingWindows class (fcest/models/sliding_windows.py),
   imported from the read-only mount with the unrelated third-party imports stubbed.
+* filtering.npz -- outputs of the REFERENCE's own highpass_filter_data (fcest/helpers/filtering.py; numpy + scipy
+  only) and of its SlidingWindows.overlapping_windowed_cov_estimation with a repetition time (filter + windows).
 * wishart_*.npz -- outputs of the CPU oracle (oracle/wishart_oracle.py).  TensorFlow / GPflow cannot be
   installed here, so these pin the *restatement* (regression fixtures), not the reference: "parity
   unpinned" for the Wishart path, as stated in the oracle header and DESIGN.md.
@@ -86,6 +88,32 @@ def make_sliding():
     print("sliding fixtures written")
 
 
+def make_filtering():
+    SlidingWindows = import_reference_sliding_windows()
+    from fcest.helpers.filtering import _butter_highpass, highpass_filter_data
+    rng = np.random.default_rng(23)
+    out = {}
+    # (tag, N, D, window length in TRs, repetition time in seconds)
+    cases = [("a", 80, 5, 9, 1.0), ("b", 150, 4, 30, 0.72), ("c", 64, 3, 15, 2.0), ("d", 19, 2, 7, 1.0),
+             ("e", 400, 6, 121, 1.0)]
+    for tag, n, d, w, tr in cases:
+        y = rng.standard_normal((n, d)) + (5.0 if tag == "b" else 0.0)
+        y += np.sin(np.linspace(0, 3, n))[:, None]  # slow drift for the high-pass to remove
+        out[f"y_{tag}"] = y
+        out[f"meta_{tag}"] = np.array([w, tr])
+        out[f"filtered_{tag}"] = highpass_filter_data(y, window_length=w, repetition_time=tr)
+        b, a = _butter_highpass(1 / (w * tr), nyquist_freq=1 / tr / 2)
+        out[f"b_{tag}"], out[f"a_{tag}"] = b, a
+        if n > 200:
+            continue  # keep the fixture small: the long case pins the filter only
+        sw = SlidingWindows(np.linspace(0, 1, n)[:, None], y, repetition_time=tr)
+        out[f"cov_{tag}"] = sw.overlapping_windowed_cov_estimation(w, repetition_time=tr)
+        out[f"corr_{tag}"] = sw.overlapping_windowed_cov_estimation(w, repetition_time=tr,
+                                                                     connectivity_metric="correlation")
+    np.savez_compressed(os.path.join(HERE, "filtering.npz"), **out)
+    print("filtering fixtures written")
+
+
 def make_wishart():
     import torch
     from oracle import wishart_oracle as wo
@@ -111,5 +139,10 @@ def make_wishart():
 
 
 if __name__ == "__main__":
-    make_wishart()
-    make_sliding()
+    which = sys.argv[1:] or ["wishart", "sliding", "filtering"]
+    if "wishart" in which:
+        make_wishart()
+    if "sliding" in which:
+        make_sliding()
+    if "filtering" in which:
+        make_filtering()

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import filter_oracle as fo
 from oracle import sliding_oracle as so
 from oracle import wishart_oracle as wo
 
@@ -228,3 +229,33 @@ def test_keras_adam_equals_torch_adam_at_zero_epsilon():
         opt.step()
         theta, m, v = wo.keras_adam_step(theta, grad, m, v, t, eps=0.0)
         assert (theta - w.detach()).abs().max() < 1e-15
+
+
+def test_filter_oracle_matches_reference_fixtures_bit_exact():
+    """oracle/filter_oracle.py against outputs of the reference's own highpass_filter_data (and its filter design)."""
+    g = np.load(os.path.join(GOLD, "filtering.npz"))
+    for tag in "abcde":
+        w, tr = int(g[f"meta_{tag}"][0]), float(g[f"meta_{tag}"][1])
+        b, a = fo.butter_highpass(1 / (w * tr), 1 / tr / 2)
+        assert np.array_equal(b, g[f"b_{tag}"]) and np.array_equal(a, g[f"a_{tag}"])
+        out = fo.highpass_filter_data(g[f"y_{tag}"], w, tr)
+        assert np.array_equal(out, g[f"filtered_{tag}"]), tag
+        if f"cov_{tag}" in g:
+            cov = so.overlapping_windowed_cov(out, w, 1)
+            assert np.abs(cov - g[f"cov_{tag}"]).max() <= 1e-13 * max(1.0, np.abs(cov).max())
+
+
+def test_host_filter_design_is_bit_identical_to_scipy():
+    """The product's host-side design (NumPy only) against scipy.signal.butter / lfilter_zi: no GPU involved."""
+    from scipy.signal import butter, lfilter_zi
+    from fcest_b200.helpers.filtering import _butter_highpass, _compute_lower_frequency_cutoff, _lfilter_zi
+    for w, tr in [(30, 1.0), (15, 2.0), (121, 0.72), (181, 1.0), (7, 1.0), (21, 0.8), (3, 1.0)]:
+        cutoff = _compute_lower_frequency_cutoff(w, tr)
+        assert cutoff == 1 / (w * tr)
+        for order in (5, 2, 3):
+            b, a = _butter_highpass(cutoff, nyquist_freq=1 / tr / 2, order=order)
+            bs, as_ = butter(order, cutoff / (1 / tr / 2), btype="high", analog=False)
+            assert np.array_equal(b, bs) and np.array_equal(a, as_) and a[0] == 1.0
+            assert np.array_equal(_lfilter_zi(b, a), lfilter_zi(bs, as_))
+    with pytest.raises(ValueError):
+        _butter_highpass(1.0, nyquist_freq=0.5)   # Wn = 2: scipy rejects it too
