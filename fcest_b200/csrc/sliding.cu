@@ -226,6 +226,235 @@ window_cov_kernel(const double* __restrict__ y, int N, int D, int w, int step, i
   }
 }
 
+// ---- bulk-store variant (step 1, even D <= 112): the default at the reference's sizes --------------------------
+// The register-store kernel above spends ~8 000 warp instructions per window, most of them address arithmetic and
+// predicates of the per-tile global stores, at two warps per scheduler (ncu: issue slots 23 % busy, 74 k cycles
+// for ~8 windows per SM).  Here a CTA of 16 warps per SM owns an even contiguous share of the windows; a finished
+// window is assembled (both triangles) in one of `nbuf` D x D shared-memory buffers with all offsets hoisted out of
+// the window loop, and leaves as ONE bulk-copy group (cp.async.bulk shared -> global, 16 KB pieces) issued by a
+// single thread: the rank-2 update and assembly of window g + 1 run underneath the store of window g.
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int WB_THREADS = 512;
+constexpr int WB_MAXM = 2;   // macro tiles per warp: 16 warps x 2 >= 28 macro tiles of D <= 112
+
+template <bool CORR>
+__global__ void __launch_bounds__(WB_THREADS, 1)
+window_cov_bulk_kernel(const double* __restrict__ y, int N, int D, int w, int G, int nbuf,
+                       double* __restrict__ out) {
+  extern __shared__ __align__(16) double sm[];
+  const int Dm = (D + 15) / 16 * 16, Pn = pitch4(Dm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int nwarps = WB_THREADS / 32;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int g0 = (int)((long long)blockIdx.x * N / gridDim.x);
+  const int Gc = (int)((long long)(blockIdx.x + 1) * N / gridDim.x) - g0;
+  if (Gc <= 0) return;
+  const int RB = w + Gc - 1, RBp = (w + G - 1 + 3) / 4 * 4;
+  double* Obuf = sm;                               // nbuf x (D x D)
+  double* Xs = sm + (size_t)nbuf * D * D;          // RBp x Pn block rows, centred in place
+  double* delta = Xs + (size_t)RBp * Pn;           // G x Dm window mean of the centred rows
+  double* isd = delta + (size_t)G * Dm;            // G x Dm 1 / sqrt(var) (CORR)
+  double* red = isd + (size_t)G * Dm;              // 16: scale guard
+  double* cen = red + 16;                          // 4 x Dm partial column sums
+  __shared__ int direct_all;
+  const int pad = w / 2, start = g0 - pad;
+  const double fact = 1.0 / (double)(w - 1), wd = (double)w;
+  {
+    const int h = Pn / 2;
+    for (int e = tid; e < RBp * h; e += WB_THREADS) {
+      const int t = e / h, d = 2 * (e - t * h);
+      const int src = start + t;
+      const bool live = t < RB && src >= 0 && src < N && d < D;
+      cp_async16(Xs + t * Pn + d, live ? y + (long long)src * D + d : y, live ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  if (tid < 16) reinterpret_cast<unsigned long long*>(red)[tid] = 0ull;
+  __syncthreads();
+  // block centre c[d] ~ mean of the block's first window: only an anchor (the result does not depend on it),
+  // so four partial sums per column in any order will do
+  for (int e = tid; e < 4 * Dm; e += WB_THREADS) {
+    const int part = e / Dm, d = e - part * Dm;
+    double s = 0.0;
+    for (int t = part; t < w; t += 4) s += Xs[t * Pn + d];
+    cen[e] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < RB * Dm; e += WB_THREADS) {
+    const int t = e / Dm, d = e - t * Dm;
+    const double c = (d < D) ? (cen[d] + cen[Dm + d] + cen[2 * Dm + d] + cen[3 * Dm + d]) / wd : 0.0;
+    Xs[t * Pn + d] -= c;
+  }
+  __syncthreads();
+  // per (window, column): mean offset d_g, two-pass variance (CORR), scale sum u^2 (-> max over columns)
+  for (int e = tid; e < Gc * Dm; e += WB_THREADS) {
+    const int g = e / Dm, d = e - g * Dm;
+    const double* xw = Xs + (size_t)g * Pn + d;
+    double a0 = 0.0, a1 = 0.0, r0 = 0.0, r1 = 0.0;
+    int t = 0;
+    for (; t + 1 < w; t += 2) {
+      const double ua = xw[t * Pn], ub = xw[(t + 1) * Pn];
+      a0 += ua; a1 += ub; r0 += ua * ua; r1 += ub * ub;
+    }
+    if (t < w) { const double ua = xw[t * Pn]; a0 += ua; r0 += ua * ua; }
+    const double dl = (a0 + a1) / wd;
+    delta[e] = dl;
+    if (CORR) {
+      double q0 = 0.0, q1 = 0.0;
+      for (t = 0; t + 1 < w; t += 2) {
+        const double va = xw[t * Pn] - dl, vb = xw[(t + 1) * Pn] - dl;
+        q0 += va * va; q1 += vb * vb;
+      }
+      if (t < w) { const double va = xw[t * Pn] - dl; q0 += va * va; }
+      const double var = (q0 + q1) * fact;
+      isd[e] = var > 0.0 ? 1.0 / sqrt(var) : 0.0;
+    }
+    atomicMax(reinterpret_cast<unsigned long long*>(red) + g, (unsigned long long)__double_as_longlong(r0 + r1));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double lo = INFINITY, hi = 0.0;
+    for (int g = 0; g < Gc; ++g) { const double v = red[g]; lo = fmin(lo, v); hi = fmax(hi, v); }
+    direct_all = !(hi <= kScaleGuard * lo);
+  }
+  __syncthreads();
+  const bool all_direct = direct_all != 0;
+  const int nbm = Dm / 16, nmac = nbm * (nbm + 1) / 2;
+  const int w4 = w & ~3;
+  // per-lane constants of this warp's macro tiles (hoisted out of the window loop)
+  int xa[WB_MAXM], xb[WB_MAXM];        // column offsets of the A / B fragments in a row of Xs
+  int od[WB_MAXM], om[WB_MAXM];        // element offsets in a D x D buffer: direct (row, col), mirror (col, row)
+  bool on[WB_MAXM], offd[WB_MAXM], rok[WB_MAXM][2], cok[WB_MAXM][2];
+#pragma unroll
+  for (int q = 0; q < WB_MAXM; ++q) {
+    const int mt = warp + q * nwarps;
+    on[q] = mt < nmac;
+    int I = 0, rem = on[q] ? mt : 0;
+    while (rem > I) { rem -= I + 1; ++I; }
+    const int J = rem;
+    xa[q] = 16 * I + gid; xb[q] = 16 * J + gid;
+    const int row = 16 * I + gid, col = 16 * J + 2 * tig;
+    od[q] = row * D + col; om[q] = col * D + row;
+    offd[q] = I != J;
+    rok[q][0] = row < D; rok[q][1] = row + 8 < D;
+    cok[q][0] = col < D; cok[q][1] = col + 8 < D;
+  }
+  double acc[WB_MAXM][2][2][2];
+  for (int g = 0; g < Gc; ++g) {
+    const double* Xw = Xs + (size_t)g * Pn;
+    if (g == 0 || all_direct) {
+#pragma unroll
+      for (int q = 0; q < WB_MAXM; ++q) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) acc[q][u][v][0] = acc[q][u][v][1] = 0.0;
+        if (!on[q]) continue;
+        const double* pa = Xw + tig * Pn + xa[q];
+        const double* pb = Xw + tig * Pn + xb[q];
+        for (int k0 = 0; k0 < w4; k0 += 4) {
+          const double a0 = pa[0], a1 = pa[8], b0 = pb[0], b1 = pb[8];
+          dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+          dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+          dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+          dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
+          pa += 4 * Pn;
+          pb += 4 * Pn;
+        }
+        if (w4 < w) {  // ragged last k-step: rows >= w belong to later windows
+          const bool live = w4 + tig < w;
+          const double a0 = live ? pa[0] : 0.0, a1 = live ? pa[8] : 0.0, b0 = live ? pb[0] : 0.0, b1 = live ? pb[8] : 0.0;
+          dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+          dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+          dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+          dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
+        }
+      }
+    } else {
+      // M_g = M_{g-1} + u_new u_new^T - u_old u_old^T: k-slot 0 = entering row, 1 = leaving row, 2, 3 = 0
+      const double* rsel = (tig == 0) ? Xw + (w - 1) * Pn : Xw - Pn;
+      const double sgn = (tig == 0) ? 1.0 : -1.0;
+#pragma unroll
+      for (int q = 0; q < WB_MAXM; ++q) {
+        if (!on[q]) continue;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        if (tig < 2) {
+          a0 = rsel[xa[q]] * sgn; a1 = rsel[xa[q] + 8] * sgn;
+          b0 = rsel[xb[q]]; b1 = rsel[xb[q] + 8];
+        }
+        dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+        dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+        dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+        dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
+      }
+    }
+    // assemble window g in shared memory (accumulators stay live for the next window)
+    if (tid == 0) { if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }  // buffer's previous window left
+    __syncthreads();
+    double* o = Obuf + (size_t)(nbuf == 2 ? (g & 1) : 0) * D * D;
+    const double* dg = delta + g * Dm;
+    const double* ig = isd + g * Dm;
+#pragma unroll
+    for (int q = 0; q < WB_MAXM; ++q) {
+      if (!on[q]) continue;
+      const int ca = xb[q] - gid + 2 * tig;   // first of this lane's columns
+      const double2 dc0 = *reinterpret_cast<const double2*>(dg + ca);
+      const double2 dc1 = *reinterpret_cast<const double2*>(dg + ca + 8);
+      double2 ic0, ic1;
+      if (CORR) {
+        ic0 = *reinterpret_cast<const double2*>(ig + ca);
+        ic1 = *reinterpret_cast<const double2*>(ig + ca + 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!rok[q][u]) continue;
+        const double tr = wd * dg[xa[q] + 8 * u];
+        const double ir = CORR ? ig[xa[q] + 8 * u] : 0.0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (!cok[q][v]) continue;
+          const double2 dc = v ? dc1 : dc0;
+          double c0 = (acc[q][u][v][0] - tr * dc.x) * fact;
+          double c1 = (acc[q][u][v][1] - tr * dc.y) * fact;
+          if (CORR) {
+            const double2 ic = v ? ic1 : ic0;
+            c0 = (c0 == 0.0) ? 0.0 : c0 * (ir * ic.x);
+            c1 = (c1 == 0.0) ? 0.0 : c1 * (ir * ic.y);
+          }
+          *reinterpret_cast<double2*>(o + od[q] + 8 * u * D + 8 * v) = make_double2(c0, c1);
+          if (offd[q]) {
+            double* m = o + om[q] + 8 * v * D + 8 * u;
+            m[0] = c0;
+            m[D] = c1;
+          }
+        }
+      }
+    }
+    fence_async_smem();   // generic-proxy writes of the window -> visible to the bulk-copy engine
+    __syncthreads();
+    if (tid == 0) {
+      double* gdst = out + (long long)(g0 + g) * D * D;
+      const uint32_t total = (uint32_t)D * D * 8u;
+      for (uint32_t off = 0; off < total; off += 16384u)
+        bulk_store(gdst + off / 8, o + off / 8, min(16384u, total - off));
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
+}
+
 // One CTA per (eval location t, window length w).  Rank-deficient windows (w - 2 < D) score -inf
 // (scipy: x outside the support of a singular covariance); otherwise the covariance of the w-1 rows
 // around t is accumulated with DMMA straight from global memory (y is L2 resident), factorised with
@@ -349,6 +578,30 @@ extern "C" int fcest_window_cov(const double* y, int N, int D, int window_length
   if (window_length < 2 || step_size < 1) return FCEST_ERR_ARGUMENT;
   const int nwin = N / step_size;
   const int Dm = (D + 15) / 16 * 16, Pn = pitch4(Dm);
+  // Bulk-store kernel: one CTA per SM, an even contiguous share of the windows each (at most 16 per CTA: the
+  // anchored update chain restarts at every block), one or two D x D staging buffers.
+  static const int use_bulk = getenv("FCEST_WCOV_IMPL") ? strcmp(getenv("FCEST_WCOV_IMPL"), "direct") != 0 : 1;
+  if (use_bulk && step_size == 1 && (D & 1) == 0 && Dm <= 112) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = N < sms ? N : sms;
+    if ((N + grid - 1) / grid > 16) grid = (N + 15) / 16;
+    const int Gt = (N + grid - 1) / grid;
+    const int RBp = (window_length + Gt - 1 + 3) / 4 * 4;
+    const size_t rest = sizeof(double) * ((size_t)RBp * Pn + 2 * (size_t)Gt * Dm + 16 + 4 * (size_t)Dm);
+    const size_t obytes = sizeof(double) * (size_t)D * D;
+    const int nbuf = (2 * obytes + rest <= 227 * 1024) ? 2 : ((obytes + rest <= 227 * 1024) ? 1 : 0);
+    if (nbuf > 0) {
+      const size_t smem_b = nbuf * obytes + rest;
+      auto kern = corr ? window_cov_bulk_kernel<true> : window_cov_bulk_kernel<false>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+      if (e != cudaSuccess) return (int)e;
+      kern<<<grid, WB_THREADS, smem_b, stream>>>(y, N, D, window_length, Gt, nbuf, out);
+      FCEST_CHECK_LAUNCH();
+      return 0;
+    }
+  }
   // windows per CTA: blocks sized so that two CTAs per SM cover all windows in one resident wave
   // (step 1 only; larger steps share too few rows for the incremental update to pay)
   int G = 1;

@@ -27,7 +27,13 @@ def test_window_cov_matches_reference_fixtures(cuda):
         assert np.abs(corr - g[f"corr_{tag}"]).max() <= 1e-12
 
 
-@pytest.mark.parametrize("N,D,w,step", [(1200, 100, 30, 1), (300, 17, 45, 2), (128, 64, 31, 1), (90, 3, 2, 1)])
+# bulk-store kernel: (1200,100,30) two staging buffers, 8-9 windows per CTA; (128,64,31) one window per CTA;
+# (2500,100,30) 16 windows per CTA over two waves; (700,112,25) widest D with one buffer; (1200,64,121) long
+# windows; (60,4,9) tiny tiles.  Register-store kernel: step 2, odd D, (1200,100,181) rows exceed shared memory
+# next to a staging buffer, (400,130,40) D > 112.
+@pytest.mark.parametrize("N,D,w,step", [(1200, 100, 30, 1), (300, 17, 45, 2), (128, 64, 31, 1), (90, 3, 2, 1),
+                                        (2500, 100, 30, 1), (700, 112, 25, 1), (1200, 64, 121, 1), (60, 4, 9, 1),
+                                        (1200, 100, 181, 1), (400, 130, 40, 1), (1200, 100, 30, 3)])
 def test_window_cov_matches_oracle(cuda, N, D, w, step):
     from fcest_b200.models import SlidingWindows
     rng = np.random.default_rng(N + D)
@@ -39,6 +45,18 @@ def test_window_cov_matches_oracle(cuda, N, D, w, step):
         assert got.shape == (N, D, D)
         assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), metric
         assert np.array_equal(got, np.swapaxes(got, 1, 2)) or np.abs(got - np.swapaxes(got, 1, 2)).max() < 1e-13
+
+
+def test_window_cov_badly_scaled_data(cuda):
+    """Scale guard (direct accumulation for blocks whose windows differ in scale) in the bulk-store kernel."""
+    from fcest_b200.models import SlidingWindows
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal((600, 20)) * np.exp(np.linspace(0, 18, 600))[:, None] + 100.0
+    sw = SlidingWindows(np.zeros((600, 1)), y)
+    got = sw.overlapping_windowed_cov_estimation(12)
+    ref = so.overlapping_windowed_cov(y, 12, 1, "covariance")
+    scale = np.abs(ref).reshape(600, -1).max(axis=1)[:, None, None]
+    assert (np.abs(got - ref) <= 1e-12 * np.maximum(scale, 1e-300)).all()
 
 
 def test_window_cov_zero_columns(cuda):
