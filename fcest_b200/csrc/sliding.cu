@@ -246,6 +246,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int WB_THREADS = 512;
+constexpr int WB_LANES = 8;  // threads that issue the bulk copies of a window
 constexpr int WB_MAXM = 2;   // macro tiles per warp: 16 warps x 2 >= 28 macro tiles of D <= 112
 
 template <bool CORR>
@@ -270,37 +271,51 @@ window_cov_bulk_kernel(const double* __restrict__ y, int N, int D, int w, int G,
   __shared__ int direct_all;
   const int pad = w / 2, start = g0 - pad;
   const double fact = 1.0 / (double)(w - 1), wd = (double)w;
-  {
-    const int h = Pn / 2;
-    for (int e = tid; e < RBp * h; e += WB_THREADS) {
-      const int t = e / h, d = 2 * (e - t * h);
-      const int src = start + t;
-      const bool live = t < RB && src >= 0 && src < N && d < D;
-      cp_async16(Xs + t * Pn + d, live ? y + (long long)src * D + d : y, live ? 16 : 0);
+  // stage the block's rows, one warp per row: 16-byte cp.async copies (zero-filled outside the data / past D)
+  for (int t = warp; t < RBp; t += nwarps) {
+    const int src = start + t;
+    const bool rowlive = t < RB && src >= 0 && src < N;
+    const double* yr = y + (long long)(rowlive ? src : 0) * D;
+    for (int d = 2 * lane; d < Pn; d += 64) {
+      const bool live = rowlive && d < D;
+      cp_async16(Xs + t * Pn + d, live ? yr + d : y, live ? 16 : 0);
     }
-    cp_async_commit();
-    cp_async_wait<0>();
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   if (tid < 16) reinterpret_cast<unsigned long long*>(red)[tid] = 0ull;
   __syncthreads();
   // block centre c[d] ~ mean of the block's first window: only an anchor (the result does not depend on it),
   // so four partial sums per column in any order will do
-  for (int e = tid; e < 4 * Dm; e += WB_THREADS) {
-    const int part = e / Dm, d = e - part * Dm;
-    double s = 0.0;
-    for (int t = part; t < w; t += 4) s += Xs[t * Pn + d];
-    cen[e] = s;
+  if (tid < 4 * 128) {
+    const int part = tid >> 7, d = tid & 127;
+    if (d < Dm) {
+      double s = 0.0;
+      for (int t = part; t < w; t += 4) s += Xs[t * Pn + d];
+      cen[part * Dm + d] = s;
+    }
   }
   __syncthreads();
-  for (int e = tid; e < RB * Dm; e += WB_THREADS) {
-    const int t = e / Dm, d = e - t * Dm;
-    const double c = (d < D) ? (cen[d] + cen[Dm + d] + cen[2 * Dm + d] + cen[3 * Dm + d]) / wd : 0.0;
-    Xs[t * Pn + d] -= c;
+  {
+    double c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = lane + 32 * i;
+      c[i] = (d < D) ? (cen[d] + cen[Dm + d] + cen[2 * Dm + d] + cen[3 * Dm + d]) / wd : 0.0;
+    }
+    for (int t = warp; t < RB; t += nwarps) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane + 32 * i;
+        if (d < Dm) Xs[t * Pn + d] -= c[i];
+      }
+    }
   }
   __syncthreads();
   // per (window, column): mean offset d_g, two-pass variance (CORR), scale sum u^2 (-> max over columns)
+  const unsigned inv_nbm = (65536u + (unsigned)(Dm >> 4) - 1u) / (unsigned)(Dm >> 4);  // exact e / Dm for e < 2048
   for (int e = tid; e < Gc * Dm; e += WB_THREADS) {
-    const int g = e / Dm, d = e - g * Dm;
+    const int g = (int)((((unsigned)e >> 4) * inv_nbm) >> 16), d = e - g * Dm;
     const double* xw = Xs + (size_t)g * Pn + d;
     double a0 = 0.0, a1 = 0.0, r0 = 0.0, r1 = 0.0;
     int t = 0;
@@ -400,9 +415,8 @@ window_cov_bulk_kernel(const double* __restrict__ y, int N, int D, int w, int G,
         dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
       }
     }
-    // assemble window g in shared memory (accumulators stay live for the next window)
-    if (tid == 0) { if (nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }  // buffer's previous window left
-    __syncthreads();
+    // assemble window g in shared memory (accumulators stay live for the next window).  Buffer g & 1 is free:
+    // the store of window g - 2 was waited for before the barrier of window g - 1.
     double* o = Obuf + (size_t)(nbuf == 2 ? (g & 1) : 0) * D * D;
     const double* dg = delta + g * Dm;
     const double* ig = isd + g * Dm;
@@ -443,16 +457,23 @@ window_cov_bulk_kernel(const double* __restrict__ y, int N, int D, int w, int G,
       }
     }
     fence_async_smem();   // generic-proxy writes of the window -> visible to the bulk-copy engine
+    // the store of window g - 1 has had the whole assembly of window g to drain; once it has left shared
+    // memory its buffer is free for window g + 1 (with one buffer: wait here, after the store, instead)
+    if (nbuf == 2 && tid < WB_LANES) bulk_wait_read<0>();
     __syncthreads();
-    if (tid == 0) {
-      double* gdst = out + (long long)(g0 + g) * D * D;
+    if (tid < WB_LANES) {   // lanes 0..7 of warp 0: one piece of the window each
       const uint32_t total = (uint32_t)D * D * 8u;
-      for (uint32_t off = 0; off < total; off += 16384u)
-        bulk_store(gdst + off / 8, o + off / 8, min(16384u, total - off));
-      bulk_commit();
+      const uint32_t piece = ((total / WB_LANES) + 15u) & ~15u;
+      const uint32_t off = (uint32_t)tid * piece;
+      if (off < total) {
+        bulk_store(out + (long long)(g0 + g) * D * D + off / 8, o + off / 8, min(piece, total - off));
+        bulk_commit();
+      }
+      if (nbuf == 1) bulk_wait_read<0>();
     }
+    if (nbuf == 1) __syncthreads();
   }
-  if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
+  if (tid < WB_LANES) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
 
 // One CTA per (eval location t, window length w).  Rank-deficient windows (w - 2 < D) score -inf
