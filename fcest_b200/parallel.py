@@ -3,7 +3,11 @@
 * independent subjects per rank (``SubjectBatch``) -- no data-path collective, ELBO sum only;
 * one subject, time points sharded over the ranks (``TimeShardedSVWP``): every rank evaluates the
   likelihood + projection on its slice of the N x S batch and the ELBO and gradients are combined with
-  SUM all-reduces (NCCL over NVLink on GPUs, gloo in the CPU tests).
+  SUM all-reduces (NCCL over NVLink on GPUs, gloo in the CPU tests);
+* one subject, latent GPs sharded for the conditional and time points sharded for the likelihood
+  (``LatentShardedSVWP``, SURVEY.md 8e option B): q_sqrt, its gradient and the three projection GEMMs split by
+  latent, the latent moments and their cotangents change layout in one all-to-all each way (48 MB in total
+  at C4), and only the small gradients are all-reduced.
 Kernels always see a rank-local slice; the collectives are issued from the host between kernel launches.
 """
 from __future__ import annotations
@@ -139,3 +143,181 @@ class TimeShardedSVWP:
                 p.grad = flat[o:o + n].reshape(p.grad.shape).clone()
                 o += n
         return elbo
+
+
+def alltoall_chunks(send: list, recv: list) -> None:
+    """``recv[q] <- send[rank]`` of rank q, for contiguous tensors of per-pair sizes (in place).
+
+    NCCL: one ``all_to_all`` (NVLink / NVSwitch).  Other backends (gloo in the CPU tests has no all-to-all):
+    batched point-to-point sends and receives."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        recv[0].copy_(send[0])
+        return
+    if dist.get_backend() == "nccl":
+        dist.all_to_all(recv, send)
+        return
+    rank = dist.get_rank()
+    recv[rank].copy_(send[rank])
+    reqs = []
+    for q in range(dist.get_world_size()):
+        if q != rank:
+            reqs.append(dist.P2POp(dist.isend, send[q], q))
+            reqs.append(dist.P2POp(dist.irecv, recv[q], q))
+    for w in dist.batch_isend_irecv(reqs):
+        w.wait()
+
+
+class LatentShardedSVWP:
+    """ONE sparse Wishart-process model over several GPUs: conditional sharded by latent GP, likelihood by time.
+
+    The SVGP projection is independent per latent r and the likelihood per time point n (SURVEY.md 8e,
+    option B).  Rank p owns the latents ``latents`` (a contiguous block of the R = D nu columns of q_mu / rows
+    of q_sqrt) and the time points ``times``.  One evaluation:
+
+      1. conditional on the own latents, all N time points: Sk_p, fvar_p = Pk Sk_p^T, fmean_p  (N, R_p);
+      2. all-to-all  (N, R_p) -> (N_p, R): every rank receives the moments of all latents on its time block;
+      3. Wishart likelihood + analytic cotangents on the own time block                        (N_p, R);
+      4. all-to-all back (N_p, R) -> (N, R_p);
+      5. backward of the conditional on the own latents: d q_sqrt[latents], d q_mu[:, latents] are complete
+         and stay local (with their Adam state, if any); d P and what follows from it are partial sums;
+      6. one flat SUM all-reduce of the ELBO and the small gradients (kernel, Z, A, lambda).
+
+    No gradient of the size of q_sqrt ever travels (TimeShardedSVWP all-reduces 402 MB at C4) and the per-latent
+    kernels (tri_syrk, tri_grad) shard too.  The single-matrix chain (Kmm, Cholesky, P, Pk) is replicated.
+    The phases are separate methods so that a single process can step several emulated ranks in lock-step
+    (tests); ``elbo_and_grad`` chains them with the real collectives.
+    """
+
+    def __init__(self, model, world: int | None = None, rank: int | None = None):
+        if not getattr(model, "_sparse", False):
+            raise NotImplementedError("latent sharding needs the sparse (SVWP) model")
+        r, w, _ = dist_env()
+        self.model = model
+        self.world = w if world is None else world
+        self.rank = r if rank is None else rank
+        self.R = model.q_mu.unconstrained.shape[1]
+        self.latent_blocks = [subject_partition(self.R, self.world, q) for q in range(self.world)]
+        lat = self.latent_blocks[self.rank]
+        self.latents = slice(lat.start, lat.stop)
+        self.q_mu_grad_local = None      # (M, R_p)
+        self.q_sqrt_grad_local = None    # (R_p, M, M)
+        lik = model.likelihood
+        lik.seed(lik._seed + 7919 * (self.rank + 1))
+        self._st = None
+
+    # ---- phases ----------------------------------------------------------------------------------
+    def small_grad_parameters(self) -> list:
+        m = self.model
+        ps = [m.kernel.variance, m.kernel.lengthscales, m.likelihood.A_scale_matrix, m.likelihood.additive_part]
+        if m.inducing_variable.Z.trainable:
+            ps.append(m.inducing_variable.Z)
+        return ps
+
+    def forward_local(self, x) -> list:
+        """Phase 1: moments of the own latents at all time points -> one (N_q, 2, R_p) chunk per rank q."""
+        from .gp import conditionals as cond
+        m = self.model
+        fmean, fvar, kl, st = cond.conditional_forward(
+            m.kernel, m.inducing_variable.Z.unconstrained, x, m.q_mu.unconstrained[:, self.latents],
+            m.q_sqrt.unconstrained[self.latents], vgp=False, want_kl=True)
+        self._st, self._kl = st, kl
+        n = x.shape[0]
+        self.time_blocks = [time_partition(n, self.world, q) for q in range(self.world)]
+        both = torch.stack([fmean, fvar], dim=1)                              # (N, 2, R_p)
+        return [both[sl].contiguous() for sl in self.time_blocks]
+
+    def recv_buffers_forward(self, dev) -> list:
+        sl = self.time_blocks[self.rank]
+        return [torch.empty((sl.stop - sl.start, 2, len(b)), dtype=torch.float64, device=dev)
+                for b in self.latent_blocks]
+
+    def likelihood_local(self, x, y, recv: list, epsilon=None) -> list:
+        """Phase 3: likelihood on the own time block with all latents -> one (N_p, 2, R_q) cotangent chunk per
+        rank q."""
+        from . import ops
+        m = self.model
+        sl = self.time_blocks[self.rank]
+        fmean = ops.as_pitched(torch.cat([c[:, 0, :] for c in recv], dim=1))  # (N_p, R)
+        fvar = ops.as_pitched(torch.cat([c[:, 1, :] for c in recv], dim=1))
+        eps = None if epsilon is None else epsilon[:, sl]
+        out = m.likelihood.variational_expectations(x[sl], fmean, fvar, y[sl].contiguous(), epsilon=eps,
+                                                    need_grad=True)
+        self._lik = out
+        g = torch.stack([out["g_fmean"], out["g_fvar"]], dim=1)                # (N_p, 2, R)
+        return [g[:, :, b.start:b.stop].contiguous() for b in self.latent_blocks]
+
+    def recv_buffers_backward(self, dev) -> list:
+        rp = len(self.latent_blocks[self.rank])
+        return [torch.empty((sl.stop - sl.start, 2, rp), dtype=torch.float64, device=dev)
+                for sl in self.time_blocks]
+
+    def backward_local(self, recv: list) -> torch.Tensor:
+        """Phase 5: backward of the conditional on the own latents; returns the flat buffer of partial sums
+        [ELBO, small gradients] for the all-reduce."""
+        from . import ops
+        from .gp import conditionals as cond
+        m = self.model
+        g_fmean = ops.as_pitched(torch.cat([c[:, 0, :] for c in recv], dim=0))  # (N, R_p)
+        g_fvar = ops.as_pitched(torch.cat([c[:, 1, :] for c in recv], dim=0))
+        need_Z = m.inducing_variable.Z.trainable
+        gr = cond.conditional_backward(self._st, g_fmean, g_fvar, need_Z=need_Z)
+        self.q_mu_grad_local, self.q_sqrt_grad_local = gr["q_mu"], gr["q_sqrt"]
+        out = self._lik
+        elbo = torch.empty(1, dtype=torch.float64, device=g_fmean.device)
+        ops.sum_into(out["ve"], out["ve"].numel(), 1, 1.0, elbo, False)
+        ops.axpby(-1.0, self._kl, 1.0, elbo)
+        parts = [elbo, gr["kvar"].reshape(-1), gr["kls"].reshape(-1), out["gA"].reshape(-1), out["glam"].reshape(-1)]
+        if need_Z:
+            parts.append(gr["Z"].reshape(-1))
+        self._infos = (out["info"], self._st.info)
+        return torch.cat(parts)
+
+    def finish(self, flat: torch.Tensor, check: bool = True) -> torch.Tensor:
+        """Phase 6 (after the all-reduce of ``flat``): scatter the small gradients into ``Parameter.grad``."""
+        from . import ops
+        m = self.model
+        lik = m.likelihood
+        kv, kls = m.kernel.variance, m.kernel.lengthscales
+        g_kvar, g_kls = flat[1:2].clone(), flat[2:3].clone()
+        kv.grad = ops.softplus_bwd(kv.unconstrained.reshape(1), g_kvar, torch.empty_like(g_kvar)).reshape(kv.shape)
+        kls.grad = ops.softplus_bwd(kls.unconstrained.reshape(1), g_kls, torch.empty_like(g_kls)).reshape(kls.shape)
+        o = 3
+        for prm in [lik.A_scale_matrix, lik.additive_part] + ([m.inducing_variable.Z] if m.inducing_variable.Z.trainable else []):
+            n = prm.unconstrained.numel()
+            prm.grad = flat[o:o + n].reshape(prm.unconstrained.shape).clone()
+            o += n
+        if check:
+            lik.check_info(self._infos[0])
+            m._check_chol(self._infos[1])
+        return flat[0].clone()
+
+    # ---- one evaluation with the real collectives ------------------------------------------------------
+    def elbo_and_grad(self, data, epsilon=None, check: bool = True) -> torch.Tensor:
+        """ELBO (identical on every rank); ``q_mu_grad_local`` / ``q_sqrt_grad_local`` hold the gradients of the
+        own latents, the small parameters' ``.grad`` are complete on every rank."""
+        x, y = self.model._data(data)
+        send = self.forward_local(x)
+        recv = self.recv_buffers_forward(x.device)
+        alltoall_chunks(send, recv)
+        send = self.likelihood_local(x, y, recv, epsilon=epsilon)
+        recv = self.recv_buffers_backward(x.device)
+        alltoall_chunks(send, recv)
+        flat = self.backward_local(recv)
+        allreduce_sum_(flat)
+        return self.finish(flat, check=check)
+
+    def gather_grads(self) -> None:
+        """All-gather the sharded gradients into ``model.q_mu.grad`` / ``model.q_sqrt.grad`` (compatibility /
+        tests; training keeps them sharded)."""
+        m = self.model
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            m.q_mu.grad, m.q_sqrt.grad = self.q_mu_grad_local, self.q_sqrt_grad_local
+            return
+        M = m.q_mu.unconstrained.shape[0]
+        dev = self.q_sqrt_grad_local.device
+        qs = [torch.empty((len(b), M, M), dtype=torch.float64, device=dev) for b in self.latent_blocks]
+        dist.all_gather(qs, self.q_sqrt_grad_local.contiguous())
+        qm = [torch.empty((len(b), M), dtype=torch.float64, device=dev) for b in self.latent_blocks]
+        dist.all_gather(qm, self.q_mu_grad_local.t().contiguous())
+        m.q_sqrt.grad = torch.cat(qs, dim=0)
+        m.q_mu.grad = torch.cat(qm, dim=0).t().contiguous()

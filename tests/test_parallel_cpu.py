@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fcest_b200.parallel import SubjectBatch, TimeShardedSVWP, subject_partition, time_partition
+from fcest_b200.parallel import (SubjectBatch, TimeShardedSVWP, alltoall_chunks, subject_partition,
+                                 time_partition)
 
 
 def test_partition_covers_every_subject_once():
@@ -136,3 +137,45 @@ def test_time_sharded_allreduce_gloo_world2():
         assert abs(elbo - (total - 10.0)) < 1e-12      # KL counted once
         assert abs(gq - total) < 1e-12                 # q_sqrt cotangent reduced inside the backward pass
         assert abs(gmu - (total - 1.0)) < 1e-12 and abs(gz - (total - 1.0)) < 1e-12
+
+
+def _a2a_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the layout change of LatentShardedSVWP: rank p holds (N, 2, R_p), rank q must end up with (N_q, 2, R)
+    N, R = 7, 5
+    full = torch.arange(N * 2 * R, dtype=torch.float64).reshape(N, 2, R)
+    lat = [subject_partition(R, world, q) for q in range(world)]
+    tim = [time_partition(N, world, q) for q in range(world)]
+    mine = full[:, :, lat[rank].start:lat[rank].stop]
+    send = [mine[tim[q]].contiguous() for q in range(world)]
+    nq = tim[rank].stop - tim[rank].start
+    recv = [torch.empty((nq, 2, len(lat[p])), dtype=torch.float64) for p in range(world)]
+    alltoall_chunks(send, recv)
+    got = torch.cat(recv, dim=2)
+    ok_fwd = bool(torch.equal(got, full[tim[rank]]))
+    # and back: (N_p, 2, R) -> (N, 2, R_p)
+    send = [got[:, :, lat[q].start:lat[q].stop].contiguous() for q in range(world)]
+    recv = [torch.empty((tim[q].stop - tim[q].start, 2, len(lat[rank])), dtype=torch.float64) for q in range(world)]
+    alltoall_chunks(send, recv)
+    ok_bwd = bool(torch.equal(torch.cat(recv, dim=0), mine))
+    out.put((rank, ok_fwd, ok_bwd))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_latent_time_alltoall_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert res == [(0, True, True), (1, True, True)]

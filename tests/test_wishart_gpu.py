@@ -248,6 +248,42 @@ def test_time_sharded_matches_single_gpu(cuda):
             assert _rel(q.grad.cpu().numpy().reshape(-1), g.cpu().numpy().reshape(-1)) < 1e-11, q.name
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_latent_sharded_matches_single_gpu(cuda, world):
+    """LatentShardedSVWP (conditional sharded by latent, likelihood by time), emulated on one GPU: the ranks'
+    phases run in lock-step and the two all-to-alls / the all-reduce are list transpositions / sums.  ELBO and
+    every gradient must equal the unsharded evaluation (sums re-associated: 1e-11)."""
+    from fcest_b200.parallel import LatentShardedSVWP
+    kind, N, D, S, M = "svgp", 50, 5, 3, 14       # R = 25: uneven, odd latent blocks
+    m, x, y, eps, p = _build(kind, N, D, S, M)
+    ref_elbo = m.elbo_and_grad((x.numpy(), y.numpy()), epsilon=eps.cuda()).item()
+    small = [m.kernel.variance, m.kernel.lengthscales, m.likelihood.A_scale_matrix, m.likelihood.additive_part,
+             m.inducing_variable.Z]
+    ref_small = [q.grad.clone() for q in small]
+    ref_qmu, ref_qsqrt = m.q_mu.grad.clone(), m.q_sqrt.grad.clone()
+    xs, ys, ec = x.cuda(), y.cuda(), eps.cuda()
+    ranks = [LatentShardedSVWP(m, world=world, rank=r) for r in range(world)]
+    sends = [sh.forward_local(xs) for sh in ranks]                                   # sends[p][q]
+    recvs = [[sends[p][q] for p in range(world)] for q in range(world)]             # all-to-all
+    for q, sh in enumerate(ranks):
+        assert [tuple(t.shape) for t in sh.recv_buffers_forward(xs.device)] == [tuple(t.shape) for t in recvs[q]]
+    sends = [sh.likelihood_local(xs, ys, recvs[r], epsilon=ec) for r, sh in enumerate(ranks)]
+    recvs = [[sends[p][q] for p in range(world)] for q in range(world)]
+    for q, sh in enumerate(ranks):
+        assert [tuple(t.shape) for t in sh.recv_buffers_backward(xs.device)] == [tuple(t.shape) for t in recvs[q]]
+    flats = [sh.backward_local(recvs[r]) for r, sh in enumerate(ranks)]
+    total = sum(flats)                                                               # all-reduce
+    for r, sh in enumerate(ranks):
+        elbo = sh.finish(total.clone()).item()
+        assert abs(elbo - ref_elbo) <= 1e-12 * abs(ref_elbo)
+        for q, g in zip(small, ref_small):
+            assert _rel(q.grad.cpu().numpy().reshape(-1), g.cpu().numpy().reshape(-1)) < 1e-11, q.name
+        lat = sh.latents
+        assert _rel(sh.q_mu_grad_local.cpu().numpy(), ref_qmu[:, lat].cpu().numpy()) < 1e-11
+        assert _rel(sh.q_sqrt_grad_local.cpu().numpy(), ref_qsqrt[lat].cpu().numpy()) < 1e-11
+    assert sum(len(b) for b in ranks[0].latent_blocks) == D * D
+
+
 @pytest.mark.parametrize("D", [7, 8, 33, 50, 56, 57])
 def test_predict_moments_all_tile_counts(cuda, D):
     """fcest_cov_moments: register-tiled kernel (D <= 56, every row-block count incl. ragged warps) and the

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""One C4 subject (SVWP N=1200 D=50 S=8 M=200) with its time points sharded over the ranks
-(fcest_b200.parallel.TimeShardedSVWP): parity of the sharded ELBO + gradients against the unsharded
+"""One C4 subject (SVWP N=1200 D=50 S=8 M=200) sharded over the ranks -- by time points
+(fcest_b200.parallel.TimeShardedSVWP, --mode time) or by latent GP for the conditional and by time for the
+likelihood (LatentShardedSVWP, --mode latent): parity of the sharded ELBO + gradients against the unsharded
 evaluation on the same noise, then strong-scaling timing (device events, max over ranks).
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
@@ -27,9 +28,10 @@ def main():
     ap.add_argument("--D", type=int, default=50)
     ap.add_argument("--S", type=int, default=8)
     ap.add_argument("--M", type=int, default=200)
+    ap.add_argument("--mode", choices=["time", "latent"], default="time")
     args = ap.parse_args()
     from fcest_b200.models import SparseVariationalWishartProcess
-    from fcest_b200.parallel import TimeShardedSVWP, dist_env
+    from fcest_b200.parallel import LatentShardedSVWP, TimeShardedSVWP, dist_env
     from oracle import wishart_oracle as wo  # input generator only
 
     rank, world, local = dist_env()
@@ -51,10 +53,14 @@ def main():
               m.likelihood.additive_part, m.inducing_variable.Z]
     ref_elbo = m.elbo_and_grad((xd, yd), epsilon=eps).item()
     ref = [q.grad.clone() for q in params]
-    sh = TimeShardedSVWP(m)
+    sh = TimeShardedSVWP(m) if args.mode == "time" else LatentShardedSVWP(m)
     elbo = sh.elbo_and_grad((xd, yd), epsilon=eps).item()
     errs = {"elbo": abs(elbo - ref_elbo) / abs(ref_elbo)}
-    for nm, q, r in zip(names, params, ref):
+    if args.mode == "latent":   # q_mu / q_sqrt gradients stay sharded: compare the own block
+        lat = sh.latents
+        errs["q_mu"] = float((sh.q_mu_grad_local - ref[0][:, lat]).abs().max() / ref[0].abs().max())
+        errs["q_sqrt"] = float((sh.q_sqrt_grad_local - ref[1][lat]).abs().max() / ref[1].abs().max())
+    for nm, q, r in list(zip(names, params, ref))[2 if args.mode == "latent" else 0:]:
         errs[nm] = float((q.grad - r).abs().max() / r.abs().max())
 
     def barrier():
@@ -76,9 +82,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     if rank == 0:
-        print(json.dumps({"mode": "time-sharded single subject (strong scaling)", "n_gpus": world, "N": N, "D": D, "S": S,
+        label = ("time-sharded" if args.mode == "time" else "latent-sharded conditional + time-sharded likelihood")
+        print(json.dumps({"mode": label + " single subject (strong scaling)", "n_gpus": world, "N": N, "D": D, "S": S,
                           "M": M, "ms_per_step": ms, "evals_per_s": 1e3 / ms, "max_rel_err_vs_unsharded": errs,
-                          "allreduce_bytes_per_step": int(8 * (D * D * (M * (M + 1) // 2 + 15) // 16 * 16))}), flush=True)
+                          "collective_bytes_per_step": (int(8 * (D * D * ((M * (M + 1) // 2 + 15) // 16 * 16))) if args.mode == "time"
+                                                        else int(2 * 2 * 8 * N * D * D))}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
