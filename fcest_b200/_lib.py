@@ -56,6 +56,7 @@ SIGNATURES = {
     "fcest_window_cv": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _d, _p, _ll, _p]),
     "fcest_filtfilt_scratch_bytes": (_ll, [_i, _ll, _i]),
     "fcest_filtfilt": (_i, [_p, _i, _ll, _p, _p, _p, _i, _p, _p, _p]),
+    "fcest_tvfc_summary": (_i, [_p, _i, _i, _i, _p, _p]),
     "fcest_launch_count": (_ll, []),
     "fcest_launch_count_add": (_ll, [_ll]),
 }

@@ -167,6 +167,13 @@ long long fcest_filtfilt_scratch_bytes(int N, long long C, int order);
 int fcest_filtfilt(const double* x, int N, long long C, const double* b, const double* a, const double* zi,
                    int order, double* scratch, double* out, cudaStream_t stream);
 
+/* ---- temporal summaries of a TVFC estimate (fcest/helpers/summary_measures.py:16-126):
+ *   cov (N, D, D) -> out (D, D).  metric 0 = nanmean, 1 = nanvar, 2 = nanstd over the time axis (sums in time
+ *   order: bit-identical to numpy), 3 = rate of change (mean_t |c_{t+1} / c_t - 1|, inf and > 10 count as 1),
+ *   4 = AR(1) coefficient of every edge series (least squares of c_{t+1} on [1, c_t]; the (i, j), i > j series
+ *   fills both triangles, the diagonal is 0). */
+int fcest_tvfc_summary(const double* cov, int N, int D, int metric, double* out, cudaStream_t stream);
+
 /* ---- instrumentation: number of kernels this library has launched since load (bench.py "gpu_launches"). */
 long long fcest_launch_count(void);
 long long fcest_launch_count_add(long long n);

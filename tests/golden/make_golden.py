@@ -6,6 +6,8 @@
   imported from the read-only mount with the unrelated third-party imports stubbed.
 * filtering.npz -- outputs of the REFERENCE's own highpass_filter_data (fcest/helpers/filtering.py; numpy + scipy
   only) and of its SlidingWindows.overlapping_windowed_cov_estimation with a repetition time (filter + windows).
+* summary.npz -- outputs of the REFERENCE's summarize_tvfc_estimates (fcest/helpers/summary_measures.py) for the
+  metrics that need no statsmodels (mean, variance, std, rate_of_change).
 * wishart_*.npz -- outputs of the CPU oracle (oracle/wishart_oracle.py).  TensorFlow / GPflow cannot be
   installed here, so these pin the *restatement* (regression fixtures), not the reference: "parity
   unpinned" for the Wishart path, as stated in the oracle header and DESIGN.md.
@@ -114,6 +116,26 @@ def make_filtering():
     print("filtering fixtures written")
 
 
+def make_summary():
+    import_reference_sliding_windows()   # installs the stubs (statsmodels among them) and the import path
+    from fcest.helpers.summary_measures import summarize_tvfc_estimates
+    rng = np.random.default_rng(31)
+    out = {}
+    for tag, n, d in [("a", 40, 4), ("b", 25, 7)]:
+        a = rng.standard_normal((n, d, d + 2))
+        c = a @ np.swapaxes(a, 1, 2) / (d + 2)
+        if tag == "b":
+            c[3, 1, 2] = c[3, 2, 1] = np.nan      # nan-aware metrics
+            c[7, 0, 4] = c[7, 4, 0] = 0.0         # division by zero in the rate of change -> inf -> 1
+            c[9:12, 5, 5] = 1e-9                  # step > 10 -> 1
+        out[f"c_{tag}"] = c
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for metric in ("mean", "variance", "std", "rate_of_change"):
+                out[f"{metric}_{tag}"] = summarize_tvfc_estimates(c, metric)
+    np.savez_compressed(os.path.join(HERE, "summary.npz"), **out)
+    print("summary fixtures written")
+
+
 def make_wishart():
     import torch
     from oracle import wishart_oracle as wo
@@ -139,7 +161,9 @@ def make_wishart():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wishart", "sliding", "filtering"]
+    which = sys.argv[1:] or ["wishart", "sliding", "filtering", "summary"]
+    if "summary" in which:
+        make_summary()
     if "wishart" in which:
         make_wishart()
     if "sliding" in which:

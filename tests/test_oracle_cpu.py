@@ -7,6 +7,7 @@ import torch
 
 from oracle import filter_oracle as fo
 from oracle import sliding_oracle as so
+from oracle import summary_oracle as smo
 from oracle import wishart_oracle as wo
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -259,3 +260,31 @@ def test_host_filter_design_is_bit_identical_to_scipy():
             assert np.array_equal(_lfilter_zi(b, a), lfilter_zi(bs, as_))
     with pytest.raises(ValueError):
         _butter_highpass(1.0, nyquist_freq=0.5)   # Wn = 2: scipy rejects it too
+
+
+def test_summary_oracle_matches_reference_fixtures_bit_exact():
+    """oracle/summary_oracle.py against outputs of the reference's summarize_tvfc_estimates; the time-ordered
+    sums the kernel uses reproduce numpy's reduction over the leading axis bit for bit."""
+    g = np.load(os.path.join(GOLD, "summary.npz"))
+    for tag in "ab":
+        c = g[f"c_{tag}"]
+        for metric in ("mean", "variance", "std", "rate_of_change"):
+            with np.errstate(all="ignore"):
+                assert np.array_equal(smo.summarize(c, metric), g[f"{metric}_{tag}"], equal_nan=True), (tag, metric)
+        s = np.zeros(c.shape[1:]); cnt = np.zeros(c.shape[1:])
+        for t in range(c.shape[0]):
+            ok = ~np.isnan(c[t]); s = s + np.where(ok, c[t], 0.0); cnt += ok
+        assert np.array_equal(s / cnt, g[f"mean_{tag}"], equal_nan=True)
+        q = np.zeros(c.shape[1:])
+        for t in range(c.shape[0]):
+            d = np.where(np.isnan(c[t]), 0.0, c[t] - s / cnt); q = q + d * d
+        assert np.array_equal(q / cnt, g[f"variance_{tag}"], equal_nan=True)
+
+
+def test_ar1_restatement_is_the_centred_ols_slope():
+    rng = np.random.default_rng(2)
+    c = rng.standard_normal((60, 3, 3)); c = c + np.swapaxes(c, 1, 2)
+    ref = smo.ar1(c)
+    y = c[:, 2, 1]; x, z = y[:-1], y[1:]
+    slope = ((x - x.mean()) * (z - z.mean())).sum() / ((x - x.mean()) ** 2).sum()
+    assert abs(ref[2, 1] - slope) < 1e-12 and ref[1, 2] == ref[2, 1] and ref[0, 0] == 0.0
