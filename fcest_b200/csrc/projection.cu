@@ -320,6 +320,21 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
       const int lo1 = GRAD ? max(kb_lo, jb0 + 1) : kb_lo, hi1 = GRAD ? kb_hi : min(kb_hi, jb0 + 1);
       const int lo = min(lo0, lo1), hi = two ? max(hi0, hi1) : hi0;
       if (lo > hi) continue;
+      // fast path (all but one panel of every pair): both tiles take the whole 24-column panel -- six k4-steps,
+      // no predicates (the generic loop below spends ~20 instructions per DMMA on its range logic)
+      if (two && kb_hi == kb_lo + 2 && (GRAD ? kb_lo >= jb0 + 1 : kb_hi <= jb0)) {
+        const double* fa = Wc + (8 * ib + gid) * TRI_PITCH + tig;
+        const double* fb = GRAD ? Lr + tig * PL + 8 * jb0 + gid : Wc + (8 * jb0 + gid) * TRI_PITCH + tig;
+#pragma unroll
+        for (int st = 0; st < TRI_KP / 4; ++st) {
+          const double a = fa[4 * st];
+          const double b0 = GRAD ? fb[4 * st * PL] : fb[4 * st];
+          const double b1 = GRAD ? fb[4 * st * PL + 8] : fb[4 * st + 8 * TRI_PITCH];
+          dmma(acc[q][0][0], acc[q][0][1], a, b0);
+          dmma(acc[q][1][0], acc[q][1][1], a, b1);
+        }
+        continue;
+      }
       const double* pa = Wc + (8 * ib + gid) * TRI_PITCH + tig - 8 * kb_lo;
       const double* pb = GRAD ? Lr + (tig - 8 * kb_lo) * PL + 8 * jb0 + gid
                               : Wc + (8 * jb0 + gid) * TRI_PITCH + tig - 8 * kb_lo;
