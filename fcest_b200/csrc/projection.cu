@@ -238,6 +238,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
   for (int e = tid; e < 2 * stage_doubles; e += blockDim.x) sm[e] = 0.0;
   __syncthreads();
 
+  double diag_pending = 0.0;   // grad: this thread's diagonal element of the panel in flight
   auto load_panel = [&](int pnl, int buf) {
     double* Wc = sm + buf * stage_doubles;                 // Mp x TRI_PITCH: column slab (L for syrk, Gs for grad)
     const int k0 = pnl * TRI_KP;
@@ -246,7 +247,9 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
       const int i0 = k0;
       for (int e = tid; e < (M - i0) * (TRI_KP / 2); e += blockDim.x) {
         const int i = i0 + e / (TRI_KP / 2), c2 = 2 * (e % (TRI_KP / 2)), k = k0 + c2;
-        int bytes = (M - k) * 8;
+        // columns k <= i (L is lower triangular: the strict upper part of the slab's diagonal square reads as
+        // zero) and k < M, through the copy size
+        int bytes = min(M - k, i - k + 1) * 8;
         bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
         cp_async16(Wc + i * TRI_PITCH + c2, bytes > 0 ? L + (long long)i * M + k : L, bytes);
       }
@@ -257,7 +260,8 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
           double* dst = Wc + i * TRI_PITCH + kk;
           if (k < M) {
             const int idx = (k <= i) ? i * (i + 1) / 2 + k : k * (k + 1) / 2 + i;
-            cp_async8(dst, G + idx);
+            if (i == k) diag_pending = G[idx];   // lands as 2 Gk_ii - kl at the top of the panel's iteration
+            else cp_async8(dst, G + idx);
           } else {
             *dst = 0.0;
           }
@@ -278,34 +282,20 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
     }
     cp_async_commit();
   };
-  // strict-upper entries of the slab's diagonal square must read as zero (L lower triangular)
-  auto mask_diag = [&](int pnl, int buf) {
-    double* Wc = sm + buf * stage_doubles;
-    const int k0 = pnl * TRI_KP;
-    if (GRAD) {
-      // grad: Lr is masked by the copy sizes above.  out = (Gs + diag(Gk_ii) - kl I) L: the packed diagonal holds
-      // W_ii (not 2 W_ii) and the KL term is -kl L, so the slab's diagonal becomes 2 Gk_ii - kl and the epilogue
-      // needs no L / G reloads
-      if (tid < TRI_KP && k0 + tid < M) {
-        double* d = Wc + (k0 + tid) * TRI_PITCH + tid;
-        *d = 2.0 * *d - kl;
-      }
-      return;
-    }
-    for (int e = tid; e < TRI_KP * TRI_KP; e += blockDim.x) {
-      const int ii = e / TRI_KP, kk = e - ii * TRI_KP;
-      if (kk > ii && k0 + ii < Mp) Wc[(k0 + ii) * TRI_PITCH + kk] = 0.0;
-    }
-  };
-
+  // One block barrier per panel: it publishes panel pnl (every thread has waited for its own copies) and says
+  // that everyone is done with panel pnl - 1, whose buffer the copies of panel pnl + 1 may now overwrite.
   load_panel(0, 0);
   for (int pnl = 0; pnl < npanels; ++pnl) {
     const int buf = pnl & 1;
-    if (pnl + 1 < npanels) load_panel(pnl + 1, buf ^ 1); else cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<0>();
+    if (GRAD && lane < TRI_KP) {
+      // out = (Gs + diag(Gk_ii) - kl I) L: the packed diagonal holds W_ii (not 2 W_ii) and the KL term is -kl L, so
+      // the slab's diagonal becomes 2 Gk_ii - kl and the epilogue needs no L / G reloads
+      const int k = pnl * TRI_KP + lane;
+      if (k < M && (k % TRI_WARPS) == warp) sm[buf * stage_doubles + k * TRI_PITCH + lane] = 2.0 * diag_pending - kl;
+    }
     __syncthreads();
-    mask_diag(pnl, buf);
-    __syncthreads();
+    if (pnl + 1 < npanels) load_panel(pnl + 1, buf ^ 1);
     const double* Wc = sm + buf * stage_doubles;
     const double* Lr = Wc + Mp * TRI_PITCH;
     const int kb_lo = 3 * pnl, kb_hi = min(nb, 3 * pnl + 3) - 1;   // blocks of this panel (inclusive)
@@ -349,7 +339,6 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
         }
       }
     }
-    __syncthreads();  // everyone is done with `buf` before it is refilled two iterations later
   }
 
   // epilogue
