@@ -363,7 +363,11 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
           if (col == row) tr += c;
         } else {
           double v = c;
-          if (col == row) v += kl / L[(long long)row * M + row];
+          // only the 25 diagonal tiles pay for the load + fp64 division (warp-uniform test first: the compiler
+          // otherwise evaluates kl / L_mm for every element, 21 % of the kernel's instructions)
+          if (jb0 + t2 == ib) {
+            if (col == row) v += kl / L[(long long)row * M + row];
+          }
           dq_sqrt[(long long)r * M * M + (long long)row * M + col] = v;
         }
       }
