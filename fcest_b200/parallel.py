@@ -306,6 +306,50 @@ class LatentShardedSVWP:
         allreduce_sum_(flat)
         return self.finish(flat, check=check)
 
+    # ---- training with sharded optimiser state ------------------------------------------------------------
+    def adam_step(self, learning_rate: float = 0.001, beta_1: float = 0.9, beta_2: float = 0.999,
+                  epsilon: float = 1e-7, update_small: bool = True) -> None:
+        """One Keras-flavoured Adam update (``helpers.inference.KerasAdam``) after ``elbo_and_grad``: the own block of
+        q_sqrt / q_mu with LOCAL first / second moments (1 / world of the 2.4 GB of Adam state at C4), the small
+        parameters replicated (their gradients are identical on every rank after the all-reduce, so the replicas
+        stay bit-identical).  ``update_small=False`` is for emulated ranks that share one model object."""
+        from . import ops
+        from .helpers.inference import KerasAdam
+        m = self.model
+        if getattr(self, "_adam_t", None) is None:
+            self._adam_t = 0
+            self._qs_local = m.q_sqrt.unconstrained[self.latents]              # contiguous view: updated in place
+            self._qm_local = m.q_mu.unconstrained[:, self.latents].contiguous()  # master copy of the own columns
+            self._mom = [torch.zeros_like(t) for t in (self._qs_local, self._qs_local, self._qm_local, self._qm_local)]
+            self._small_opt = KerasAdam([p for p in self.small_grad_parameters() if p.trainable],
+                                        learning_rate, beta_1, beta_2, epsilon)
+        self._adam_t += 1
+        kw = dict(grad_sign=-1.0, lr=learning_rate, b1=beta_1, b2=beta_2, eps=epsilon)
+        if m.q_sqrt.trainable:
+            ops.adam_step(self._qs_local, self.q_sqrt_grad_local.contiguous(), self._mom[0], self._mom[1],
+                          self._adam_t, **kw)
+        if m.q_mu.trainable:
+            ops.adam_step(self._qm_local, self.q_mu_grad_local.contiguous(), self._mom[2], self._mom[3],
+                          self._adam_t, **kw)
+            m.q_mu.unconstrained[:, self.latents] = self._qm_local
+        if update_small:
+            self._small_opt.step()
+
+    def gather_parameters(self) -> None:
+        """All-gather the trained q_mu / q_sqrt blocks so that every rank holds the full model (prediction,
+        ``save_model_params_dict``)."""
+        m = self.model
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            return
+        M = m.q_mu.unconstrained.shape[0]
+        dev = m.q_sqrt.unconstrained.device
+        qs = [torch.empty((len(b), M, M), dtype=torch.float64, device=dev) for b in self.latent_blocks]
+        dist.all_gather(qs, m.q_sqrt.unconstrained[self.latents].contiguous())
+        qm = [torch.empty((len(b), M), dtype=torch.float64, device=dev) for b in self.latent_blocks]
+        dist.all_gather(qm, m.q_mu.unconstrained[:, self.latents].t().contiguous())
+        m.q_sqrt.unconstrained.copy_(torch.cat(qs, dim=0))
+        m.q_mu.unconstrained.copy_(torch.cat(qm, dim=0).t())
+
     def gather_grads(self) -> None:
         """All-gather the sharded gradients into ``model.q_mu.grad`` / ``model.q_sqrt.grad`` (compatibility /
         tests; training keeps them sharded)."""

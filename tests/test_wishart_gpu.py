@@ -284,6 +284,37 @@ def test_latent_sharded_matches_single_gpu(cuda, world):
     assert sum(len(b) for b in ranks[0].latent_blocks) == D * D
 
 
+def test_latent_sharded_adam_matches_single_gpu_trajectory(cuda):
+    """Three Adam steps with sharded q_sqrt / q_mu optimiser state (two emulated ranks in lock-step) against the
+    unsharded KerasAdam trajectory on the same noise."""
+    from fcest_b200.helpers.inference import KerasAdam
+    from fcest_b200.parallel import LatentShardedSVWP
+    kind, N, D, S, M = "svgp", 40, 4, 3, 10
+    world, steps = 2, 3
+    m_ref, x, y, eps, p = _build(kind, N, D, S, M)
+    m_sh, *_ = _build(kind, N, D, S, M)
+    xs, ys = x.cuda(), y.cuda()
+    g = torch.Generator().manual_seed(9)
+    noise = [torch.randn(S, N, D * D, dtype=torch.float64, generator=g).cuda() for _ in range(steps)]
+    opt = KerasAdam(m_ref.trainable_parameters)
+    ranks = [LatentShardedSVWP(m_sh, world=world, rank=r) for r in range(world)]
+    for it in range(steps):
+        m_ref.elbo_and_grad((xs, ys), epsilon=noise[it])
+        opt.step()
+        sends = [sh.forward_local(xs) for sh in ranks]
+        recvs = [[sends[p_][q] for p_ in range(world)] for q in range(world)]
+        sends = [sh.likelihood_local(xs, ys, recvs[r], epsilon=noise[it]) for r, sh in enumerate(ranks)]
+        recvs = [[sends[p_][q] for p_ in range(world)] for q in range(world)]
+        flats = [sh.backward_local(recvs[r]) for r, sh in enumerate(ranks)]
+        total = sum(flats)
+        for r, sh in enumerate(ranks):
+            sh.finish(total.clone())
+        for r, sh in enumerate(ranks):
+            sh.adam_step(update_small=(r == 0))     # the emulated ranks share one model object
+    for a, b in zip(m_ref.parameters, m_sh.parameters):
+        assert _rel(b.unconstrained.cpu().numpy().reshape(-1), a.unconstrained.cpu().numpy().reshape(-1)) < 1e-9, a.name
+
+
 @pytest.mark.parametrize("D", [7, 8, 33, 50, 56, 57])
 def test_predict_moments_all_tile_counts(cuda, D):
     """fcest_cov_moments: register-tiled kernel (D <= 56, every row-block count incl. ragged warps) and the
