@@ -95,7 +95,9 @@ class SlidingWindows:
         stage = cls._pinned[:t.numel()].view(t.shape)
         stage.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return stage.numpy().copy()
+        # pinned staging -> caller-owned pageable memory with torch's multi-threaded copy (numpy's single-threaded
+        # .copy() of the 96 MB result cost more than the kernel and the PCIe transfer together)
+        return torch.empty(t.shape, dtype=torch.float64).copy_(stage).numpy()
 
     def compute_cross_validated_optimal_window_length(
             self,
