@@ -88,7 +88,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -226,8 +226,6 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's version / debug banner goes to stdout by default: keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
 
@@ -370,12 +368,21 @@ def run_cuda(args):
                 "value": 1.0 / min(ts), "unit": "evals/s", "cores": threads, "kind": "port",
                 "sample": "3 full C4 evaluations (1 warm-up, best of 2) of the torch-CPU float64 restatement of the "
                           "reference's TF/GPflow op sequence (oracle/wishart_oracle.py); not TensorFlow"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version
+    # banner there when NCCL_DEBUG is set on the box) are sent to stderr; the JSON goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
