@@ -5,11 +5,12 @@
 // cov -> corr with corr[cov == 0] = 0, fcest/helpers/array_operations.py:37-53) and :219-272
 // (leave-centre-out window covariance + zero-mean MVN log density of the held-out row).
 //
-// window_cov_kernel: one CTA per output window; the window is staged (centred) in shared memory and
-// the D x D Gram matrix is produced on the fp64 tensor pipe, each CTA writing its 8 D^2 bytes in
-// 64-byte row segments.  Output traffic (8 N D^2 bytes, 96 MB at N=1200, D=100) bounds the kernel.
-// Each window is computed directly (two-pass), NOT by differencing prefix sums: the reference's
-// 1e-12 tolerance does not survive a global prefix-sum on non-centred data.
+// window_cov: output traffic (8 N D^2 bytes, 96 MB at N=1200, D=100) bounds the estimator.  Two kernels share the
+// anchored prefix-sum formulation described below (a block of consecutive windows per CTA, re-anchored by a direct
+// two-pass accumulation at every block start -- a GLOBAL prefix sum would not survive the reference's 1e-12
+// tolerance on non-centred data):
+//   window_cov_bulk_kernel  step 1, even D <= 112: windows assembled in shared memory and written with cp.async.bulk
+//   window_cov_kernel       everything else: 64-byte row segments straight from the accumulator registers
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
