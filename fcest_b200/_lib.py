@@ -32,6 +32,7 @@ SIGNATURES = {
     "fcest_pack_outer": (_i, [_p, _ll, _i, _i, _p, _ll, _p, _p, _i, _p]),
     "fcest_tri_syrk_pack": (_i, [_p, _i, _i, _p, _ll, _p, _p]),
     "fcest_tri_grad": (_i, [_p, _ll, _p, _i, _i, _p, _d, _p]),
+    "fcest_tri_grad_adam": (_i, [_p, _ll, _p, _i, _i, _d, _p, _p, _p, _d, _d, _d, _p]),
     "fcest_sym_matvec": (_i, [_p, _ll, _p, _ll, _i, _i, _p, _ll, _i, _i, _p, _ll, _p, _i, _p]),
     "fcest_matern52": (_i, [_p, _i, _p, _i, _i, _p, _p, _d, _p, _ll, _p]),
     "fcest_matern52_bwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _i, _p]),

@@ -15,6 +15,19 @@ extern "C" long long fcest_launch_count_add(long long n);
 
 namespace fcest {
 
+// Keras-flavoured Adam on one element (tf.optimizers.Adam as run_adam applies it): alpha_t = lr sqrt(1 - b2^t) /
+// (1 - b1^t), epsilon outside the square root.  One definition for the stand-alone kernel and for the update fused
+// into tri_grad's epilogue, so that both produce the same bits.
+__device__ __forceinline__ void adam_update(double& theta, double& m, double& v, double g, double alpha_t, double b1,
+                                            double b2, double eps) {
+  const double mi = m + (g - m) * (1.0 - b1);
+  const double vi = v + (g * g - v) * (1.0 - b2);
+  m = mi;
+  v = vi;
+  theta -= alpha_t * mi / (sqrt(vi) + eps);
+}
+
+
 // fp64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
 // Fragment ownership (lane = 4*gid + tig): a = A[gid][tig], b = B[tig][gid],
 // c0/c1 = C[gid][2*tig], C[gid][2*tig+1].

@@ -201,11 +201,21 @@ __device__ __forceinline__ int tri_pair_decode(int u) {
   }
 }
 
-template <bool GRAD>
+// ADAM (with GRAD): instead of writing d ELBO / d q_sqrt, the epilogue applies the Keras-Adam update of run_adam to
+// the lower triangle of q_sqrt in place (first / second moments am, av; step size from the device scalar
+// alpha_dev): the 8 M^2 R byte gradient is never written or re-read and the optimiser touches half of q_sqrt, m, v.
+struct TriAdam {
+  double* m;
+  double* v;
+  const double* alpha_dev;
+  double b1, b2, eps;
+};
+
+template <bool GRAD, bool ADAM = false>
 __global__ void __launch_bounds__(TRI_WARPS * 32, 1)
 tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __restrict__ Gk,
                       double* __restrict__ out_packed, long long ldk, double* __restrict__ klp,
-                      double* __restrict__ dq_sqrt, double kl) {
+                      double* __restrict__ dq_sqrt, double kl, TriAdam ad = TriAdam()) {
   extern __shared__ __align__(16) double sm[];
   const int Mp = (M + 7) / 8 * 8, nb = Mp / 8;
   const int PL = Mp + 4;                                   // pitch of the L row panel (GRAD)
@@ -368,7 +378,17 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
           if (jb0 + t2 == ib) {
             if (col == row) v += kl / L[(long long)row * M + row];
           }
-          dq_sqrt[(long long)r * M * M + (long long)row * M + col] = v;
+          const long long off = (long long)r * M * M + (long long)row * M + col;
+          if (ADAM) {
+            double* theta = const_cast<double*>(q_sqrt);   // every element is read (above) before it is written
+            double th = theta[off], mi = ad.m[off], vi = ad.v[off];
+            adam_update(th, mi, vi, -v, ad.alpha_dev[0], ad.b1, ad.b2, ad.eps);   // v = d ELBO / d theta: minimise -ELBO
+            ad.m[off] = mi;
+            ad.v[off] = vi;
+            theta[off] = th;
+          } else {
+            dq_sqrt[off] = v;
+          }
         }
       }
     }
@@ -381,7 +401,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
     tr = block_sum(tr, red);
     ld = block_sum(ld, red);
     if (tid == 0) { klp[2 * r] = tr; klp[2 * r + 1] = ld; }
-  } else {
+  } else if (!ADAM) {
     // strict upper triangle of dq_sqrt is zero
     double* o = dq_sqrt + (long long)r * M * M;
     for (int e = tid; e < M * M; e += blockDim.x) {
@@ -499,6 +519,25 @@ extern "C" int fcest_tri_grad(const double* Gk, long long ldk, const double* q_s
     return 0;
   }
   tri_grad_kernel<<<R, 256, 0, stream>>>(Gk, ldk, q_sqrt, M, dq_sqrt, kl);
+  FCEST_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int fcest_tri_grad_adam(const double* Gk, long long ldk, double* q_sqrt, int R, int M, double kl,
+                                   double* m, double* v, const double* alpha_t, double b1, double b2, double eps,
+                                   cudaStream_t stream) {
+  if (R <= 0) return 0;
+  if (!Gk || !q_sqrt || !m || !v || !alpha_t) return FCEST_ERR_ARGUMENT;
+  if (!(M <= 200 && (M & 1) == 0)) return FCEST_ERR_UNSUPPORTED;   // caller falls back to tri_grad + adam_step
+  const int Mp = (M + 7) / 8 * 8;
+  const size_t smem = sizeof(double) * 2 * ((size_t)Mp * TRI_PITCH + (size_t)TRI_KP * (Mp + 4));
+  cudaError_t e = cudaFuncSetAttribute(tri_stationary_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  TriAdam ad;
+  ad.m = m; ad.v = v; ad.alpha_dev = alpha_t; ad.b1 = b1; ad.b2 = b2; ad.eps = eps;
+  tri_stationary_kernel<true, true><<<R, TRI_WARPS * 32, smem, stream>>>(q_sqrt, M, Gk, nullptr, ldk, nullptr, nullptr,
+                                                                         kl, ad);
   FCEST_CHECK_LAUNCH();
   return 0;
 }

@@ -374,12 +374,11 @@ __global__ void adam_kernel(double* __restrict__ theta, const double* __restrict
   if (alpha_dev != nullptr) alpha_t = alpha_dev[0];
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
-    const double g = sign * grad[e];
-    const double mi = m[e] + (g - m[e]) * (1.0 - b1);
-    const double vi = v[e] + (g * g - v[e]) * (1.0 - b2);
+    double th = theta[e], mi = m[e], vi = v[e];
+    adam_update(th, mi, vi, sign * grad[e], alpha_t, b1, b2, eps);
     m[e] = mi;
     v[e] = vi;
-    theta[e] -= alpha_t * mi / (sqrt(vi) + eps);
+    theta[e] = th;
   }
 }
 

@@ -122,7 +122,7 @@ def conditional_forward(kernel, Z, X, q_mu, q_sqrt, vgp: bool, want_kl: bool = T
 
 
 def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: bool = True,
-                         kl_scale: float = 1.0, gk_reduce=None):
+                         kl_scale: float = 1.0, gk_reduce=None, q_sqrt_adam: dict | None = None):
     """Adjoint of ``conditional_forward`` (+ minus the KL gradient): given d ELBO / d (fmean, fvar)
     returns d ELBO / d {q_mu, q_sqrt, kvar, kls, Z} (constrained kernel parameters).
 
@@ -130,7 +130,11 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
     slice of time points.  ``gk_reduce`` (an in-place SUM all-reduce) is applied to the packed
     d ELBO / d S_r = g_var^T Pk *before* the per-latent ``tri_grad``, so d q_sqrt comes out complete
     and identical on every rank (402 MB on the wire at C4 instead of the 800 MB dense gradient);
-    ``kl_scale`` = 1 / world weights the KL part of the *other* gradients, which the caller sums over ranks."""
+    ``kl_scale`` = 1 / world weights the KL part of the *other* gradients, which the caller sums over ranks.
+
+    ``q_sqrt_adam`` = dict(m, v, alpha_dev, b1, b2, eps): apply the optimiser's update to q_sqrt inside
+    ``tri_grad``'s epilogue (``fcest_tri_grad_adam``) instead of returning the dense gradient -- SURVEY.md 8f row 1:
+    the 8 M^2 R byte gradient never round-trips through HBM.  The returned ``"q_sqrt"`` is then ``None``."""
     dev = g_fmean.device
     M, N = st.P.shape
     R = st.q_mu.shape[1]
@@ -144,7 +148,8 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     Gk = torch.empty((R, ldk), dtype=F64, device=dev)
-    dq_sqrt = torch.empty_like(st.q_sqrt)
+    fuse = q_sqrt_adam is not None and M <= 200 and M % 2 == 0   # what fcest_tri_grad_adam supports
+    dq_sqrt = None if fuse else torch.empty_like(st.q_sqrt)
     chain_stream = side if OVERLAP_BACKWARD else main
     if OVERLAP_BACKWARD:
         side.wait_stream(main)
@@ -152,7 +157,12 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
         ops.dgemm(False, False, R, K, N, g_fvar, st.Pk, Gk)
         if gk_reduce is not None:
             gk_reduce(Gk)
-        ops.call("fcest_tri_grad", ops.ptr(Gk), ldk, ops.ptr(st.q_sqrt), R, M, ops.ptr(dq_sqrt), kl)
+        if fuse:
+            a = q_sqrt_adam
+            ops.call("fcest_tri_grad_adam", ops.ptr(Gk), ldk, ops.ptr(st.q_sqrt), R, M, kl, ops.ptr(a["m"]),
+                     ops.ptr(a["v"]), ops.ptr(a["alpha_dev"]), float(a["b1"]), float(a["b2"]), float(a["eps"]))
+        else:
+            ops.call("fcest_tri_grad", ops.ptr(Gk), ldk, ops.ptr(st.q_sqrt), R, M, ops.ptr(dq_sqrt), kl)
     Gk.record_stream(chain_stream)
     del Gk
 

@@ -34,6 +34,16 @@ class KerasAdam:
             ops.adam_step(p.unconstrained, g.reshape(p.unconstrained.shape), m, v, self.t, grad_sign=-1.0,
                           lr=self.lr, b1=self.b1, b2=self.b2, eps=self.eps)
 
+    def fused_state(self, parameter) -> dict | None:
+        """Optimiser state of ``parameter`` in the form ``elbo_and_grad(q_sqrt_adam=...)`` takes (the update of
+        q_sqrt fused into the backward pass); needs the device-resident step size, i.e. ``advance()`` first."""
+        for p, m, v in zip(self.parameters, self.m, self.v):
+            if p is parameter:
+                if getattr(self, "alpha_dev", None) is None:
+                    self.alpha_dev = torch.empty(1, dtype=torch.float64, device=p.unconstrained.device)
+                return {"m": m, "v": v, "alpha_dev": self.alpha_dev, "b1": self.b1, "b2": self.b2, "eps": self.eps}
+        return None
+
     # -- CUDA-graph friendly form: the step size lives in a device scalar --------------------------------
     def advance(self) -> None:
         """Advance the step counter and refresh the device-resident bias-corrected step size."""
@@ -64,8 +74,9 @@ class GraphedTrainingStep:
     replay.  Cholesky status is checked by ``check()`` (a host sync) instead of every step.
     """
 
-    def __init__(self, model, data, optimizer: KerasAdam):
+    def __init__(self, model, data, optimizer: KerasAdam, fuse_q_sqrt: bool = True):
         self.model, self.opt = model, optimizer
+        self.fuse = fuse_q_sqrt and getattr(model, "_sparse", False)   # VGP.elbo: M = N is rarely <= 200; keep it simple
         self.x, self.y = model._data(data)
         lik = model.likelihood
         self.eps = torch.empty((lik.num_mc_samples, self.y.shape[0], lik.D * lik.nu), dtype=torch.float64,
@@ -75,7 +86,9 @@ class GraphedTrainingStep:
         self.calls = 0
 
     def _body(self):
-        elbo = self.model.elbo_and_grad((self.x, self.y), epsilon=self.eps, check=False)
+        # q_sqrt (all but a few MB of the parameters) is updated inside the backward pass; the rest by step_device()
+        fused = self.opt.fused_state(self.model.q_sqrt) if (self.fuse and self.model.q_sqrt.trainable) else None
+        elbo = self.model.elbo_and_grad((self.x, self.y), epsilon=self.eps, check=False, q_sqrt_adam=fused)
         self.opt.step_device()
         return elbo
 

@@ -119,13 +119,15 @@ class _WishartProcessBase:
         return -self.elbo(data)
 
     def elbo_and_grad(self, data=None, epsilon=None, check: bool = True, kl_scale: float = 1.0,
-                      gk_reduce=None) -> torch.Tensor:
+                      gk_reduce=None, q_sqrt_adam: dict | None = None) -> torch.Tensor:
         """One ELBO evaluation + gradient w.r.t. every trainable variable (the `eval` of the metric).
 
         Gradients (d ELBO / d unconstrained) land in ``Parameter.grad``; returns the ELBO (device scalar).
         ``kl_scale`` / ``gk_reduce`` are the hooks of the time-sharded multi-GPU evaluation
         (``fcest_b200.parallel.TimeShardedSVWP``): the KL term is weighted 1 / world on every rank and the
-        packed q_sqrt cotangent is all-reduced inside the backward pass.
+        packed q_sqrt cotangent is all-reduced inside the backward pass.  ``q_sqrt_adam`` (see
+        ``conditional_backward``) fuses the optimiser's q_sqrt update into the backward pass; ``q_sqrt.grad`` is then
+        ``None`` and q_sqrt has already moved when this returns.
         """
         x, y = self._data(data)
         lik = self.likelihood
@@ -136,7 +138,7 @@ class _WishartProcessBase:
         ops.axpby(-float(kl_scale), kl, 1.0, elbo)
         need_Z = self._sparse and self.inducing_variable.Z.trainable
         g = cond.conditional_backward(st, out["g_fmean"], out["g_fvar"], need_Z=need_Z, kl_scale=float(kl_scale),
-                                      gk_reduce=gk_reduce)
+                                      gk_reduce=gk_reduce, q_sqrt_adam=q_sqrt_adam)
         self.q_mu.grad = g["q_mu"]
         self.q_sqrt.grad = g["q_sqrt"]
         kv, kl_ = self.kernel.variance, self.kernel.lengthscales

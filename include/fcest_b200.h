@@ -73,6 +73,12 @@ int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* Sk, long lon
                         double* kl_parts, cudaStream_t stream);
 int fcest_tri_grad(const double* Gk, long long ldk, const double* q_sqrt, int R, int M,
                    double* dq_sqrt, double kl, cudaStream_t stream);
+/*   tri_grad_adam : tri_grad with the Keras-Adam update of run_adam (fcest/helpers/inference.py:72-74,111-116) fused
+ *                   into its epilogue: q_sqrt (R,M,M) is updated in place on its lower triangle, m / v are its Adam
+ *                   moments, alpha_t the bias-corrected step size in a DEVICE scalar (as fcest_adam_step_dev); the
+ *                   dense gradient is never materialised.  M <= 200 and even, else FCEST_ERR_UNSUPPORTED. */
+int fcest_tri_grad_adam(const double* Gk, long long ldk, double* q_sqrt, int R, int M, double kl, double* m,
+                        double* v, const double* alpha_t, double b1, double b2, double eps, cudaStream_t stream);
 int fcest_sym_matvec(const double* Tk, long long ldk, const double* P, long long ldp, int M, int N,
                      const double* g_var, long long ldg, int R, int use_prior, double* dP,
                      long long lddp, double* gs_out, int accumulate, cudaStream_t stream);

@@ -381,3 +381,28 @@ def test_cuda_graph_training_step_matches_eager(cuda, kind):
     (e0, mu0, sq0, ls0), (e1, mu1, sq1, ls1) = traj
     assert np.allclose(e0, e1, rtol=1e-13, atol=0.0), (e0, e1)
     assert _rel(mu1, mu0) < 1e-13 and _rel(sq1, sq0) < 1e-13 and abs(ls1 - ls0) < 1e-14
+
+
+def test_fused_q_sqrt_adam_is_bit_identical(cuda):
+    """fcest_tri_grad_adam (Adam update of q_sqrt inside tri_grad's epilogue) against tri_grad + fcest_adam_step_dev:
+    same trajectory bit for bit; the strict upper triangle of q_sqrt and of its moments is never touched."""
+    from fcest_b200.helpers.inference import GraphedTrainingStep, KerasAdam
+    N, D, S, M = 60, 6, 2, 40
+    out = []
+    for fuse in (False, True):
+        m, x, y, eps, p = _build("svgp", N, D, S, M)
+        m.likelihood.seed(5)
+        opt = KerasAdam(m.trainable_parameters)
+        g = GraphedTrainingStep(m, (x.numpy(), y.numpy()), opt, fuse_q_sqrt=fuse)
+        elbos = [float(g().item()) for _ in range(4)]
+        g.check()
+        idx = [i for i, q in enumerate(opt.parameters) if q is m.q_sqrt][0]
+        out.append((elbos, m.q_sqrt.unconstrained.cpu().numpy().copy(), opt.m[idx].cpu().numpy().copy(),
+                    opt.v[idx].cpu().numpy().copy(), m.q_mu.unconstrained.cpu().numpy().copy()))
+        assert (m.q_sqrt.grad is None) == fuse
+    a, b = out
+    assert a[0] == b[0]
+    for u, w in zip(a[1:], b[1:]):
+        assert np.array_equal(u, w)
+    iu = np.triu_indices(M, k=1)
+    assert not b[1][:, iu[0], iu[1]].any() and not b[2][:, iu[0], iu[1]].any() and not b[3][:, iu[0], iu[1]].any()
