@@ -179,7 +179,11 @@ tri_grad_kernel(const double* __restrict__ Gk, long long ldk, const double* __re
 //              dq_sqrt = tril(out + diag(Gk_ii) L - kl L) + kl diag(1/L_mm)      (2 W = Gs + diag(Gk_ii))
 // ---------------------------------------------------------------------------------------------
 constexpr int TRI_WARPS = 16;
-constexpr int TRI_KP = 24;          // panel width (3 blocks of 8)
+#ifndef FCEST_TRI_KP
+#define FCEST_TRI_KP 24
+#endif
+constexpr int TRI_KP = FCEST_TRI_KP;  // panel width (TRI_KB blocks of 8)
+constexpr int TRI_KB = TRI_KP / 8;
 constexpr int TRI_PITCH = TRI_KP + 4;
 constexpr int TRI_MAXPAIRS = 11;    // ceil(169 / 16) pairs per warp at nb = 25
 
@@ -226,7 +230,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int npairs = (nb / 2) * (nb / 2 + 1) + ((nb & 1) ? nb / 2 + 1 : 0);
-  const int npanels = (nb + 2) / 3;
+  const int npanels = (nb + TRI_KB - 1) / TRI_KB;
 
   // (ib, jb0) of this warp's pairs, 10 bits each (ib << 5 | jb0; 1023 = none), three per register
   unsigned pairs3[(TRI_MAXPAIRS + 2) / 3];
@@ -308,7 +312,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
     if (pnl + 1 < npanels) load_panel(pnl + 1, buf ^ 1);
     const double* Wc = sm + buf * stage_doubles;
     const double* Lr = Wc + Mp * TRI_PITCH;
-    const int kb_lo = 3 * pnl, kb_hi = min(nb, 3 * pnl + 3) - 1;   // blocks of this panel (inclusive)
+    const int kb_lo = TRI_KB * pnl, kb_hi = min(nb, TRI_KB * pnl + TRI_KB) - 1;   // blocks of this panel (inclusive)
 #pragma unroll
     for (int q = 0; q < TRI_MAXPAIRS; ++q) {
       const unsigned pr = (pairs3[q / 3] >> (10 * (q % 3))) & 1023u;
@@ -322,7 +326,7 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
       if (lo > hi) continue;
       // fast path (all but one panel of every pair): both tiles take the whole 24-column panel -- six k4-steps,
       // no predicates (the generic loop below spends ~20 instructions per DMMA on its range logic)
-      if (two && kb_hi == kb_lo + 2 && (GRAD ? kb_lo >= jb0 + 1 : kb_hi <= jb0)) {
+      if (two && kb_hi == kb_lo + TRI_KB - 1 && (GRAD ? kb_lo >= jb0 + 1 : kb_hi <= jb0)) {
         const double* fa = Wc + (8 * ib + gid) * TRI_PITCH + tig;
         const double* fb = GRAD ? Lr + tig * PL + 8 * jb0 + gid : Wc + (8 * jb0 + gid) * TRI_PITCH + tig;
 #pragma unroll
