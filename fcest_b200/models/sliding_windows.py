@@ -5,18 +5,20 @@ Same class, constructor and method names / defaults as the reference
 cross-validated window search run in ``fcest_window_cov`` / ``fcest_window_cv``; inputs and outputs stay
 NumPy / pandas as in the reference.  The optional Butterworth high-pass filter the reference applies when
 ``repetition_time`` is passed to ``overlapping_windowed_cov_estimation`` runs on the device too
-(``fcest_filtfilt``, ``helpers/filtering.py``), so the data makes one trip to HBM.  Out of scope here
-(SURVEY.md 2.1 row 8): CSV save / load.
+(``fcest_filtfilt``, ``helpers/filtering.py``), so the data makes one trip to HBM.  ``save_tvfc_estimates`` /
+``load_tvfc_estimates`` keep the reference's CSV layout (one row per matrix entry, one column per time step).
 """
 from __future__ import annotations
 
 import logging
+import os
 
 import numpy as np
 import pandas as pd
 import torch
 
 from .. import ops
+from ..helpers.data import to_3d_format
 from ..helpers.filtering import highpass_filter_data
 
 # scipy.stats._multivariate._eigvalsh_to_eps: 1e6 * eps relative eigenvalue threshold for "singular"
@@ -170,3 +172,32 @@ class SlidingWindows:
             idx = np.arange(int(i_window * window_length), int((i_window + 1) * window_length))
             cov_structure[idx, :, :] = np.cov(self.y_train[idx, :].T)
         return cov_structure
+
+    def save_tvfc_estimates(
+            self,
+            optimal_window_length: int,
+            savedir: str, model_name: str,
+            repetition_time: float = None,
+            connectivity_metric: str = 'correlation',
+    ) -> None:
+        """Estimate at the train locations and write the (D*D, N) table as CSV (sliding_windows.py:374-406)."""
+        train_loc_cov_structure = self.overlapping_windowed_cov_estimation(
+            window_length=optimal_window_length,
+            repetition_time=repetition_time,
+            connectivity_metric=connectivity_metric
+        )  # (N_train, D, D)
+        cov_structure_df = pd.DataFrame(
+            train_loc_cov_structure.reshape(len(train_loc_cov_structure), -1).T
+        )  # (D*D, N)
+        if not os.path.exists(savedir):
+            os.makedirs(savedir)
+        cov_structure_df.to_csv(os.path.join(savedir, model_name))
+        logging.info(f"Saved SW-CV model (train location) estimates to '{savedir:s}'.")
+
+    @staticmethod
+    def load_tvfc_estimates(savedir: str, model_name: str) -> np.array:
+        """Read a table written by ``save_tvfc_estimates`` (sliding_windows.py:408-427).  As in the reference the
+        file is read without ``index_col``, so the row index that ``to_csv`` wrote comes back as a leading column and
+        the result has N + 1 leading slices (slice 0 holds the row numbers); callers of the reference drop it."""
+        train_loc_cov_structure = pd.read_csv(os.path.join(savedir, model_name))  # (D*D, N + 1)
+        return to_3d_format(train_loc_cov_structure)

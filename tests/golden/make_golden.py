@@ -8,6 +8,8 @@
   only) and of its SlidingWindows.overlapping_windowed_cov_estimation with a repetition time (filter + windows).
 * summary.npz -- outputs of the REFERENCE's summarize_tvfc_estimates (fcest/helpers/summary_measures.py) for the
   metrics that need no statsmodels (mean, variance, std, rate_of_change).
+* tvfc_reference.csv / tvfc_csv.npz -- a file written by the REFERENCE's SlidingWindows.save_tvfc_estimates and
+  what its load_tvfc_estimates reads back from it.
 * wishart_*.npz -- outputs of the CPU oracle (oracle/wishart_oracle.py).  TensorFlow / GPflow cannot be
   installed here, so these pin the *restatement* (regression fixtures), not the reference: "parity
   unpinned" for the Wishart path, as stated in the oracle header and DESIGN.md.
@@ -136,6 +138,22 @@ def make_summary():
     print("summary fixtures written")
 
 
+def make_csv():
+    """The reference's CSV round trip: save_tvfc_estimates -> file text, load_tvfc_estimates -> array."""
+    import tempfile
+    SlidingWindows = import_reference_sliding_windows()
+    rng = np.random.default_rng(41)
+    y = rng.standard_normal((12, 3))
+    sw = SlidingWindows(np.linspace(0, 1, 12)[:, None], y)
+    with tempfile.TemporaryDirectory() as d:
+        sw.save_tvfc_estimates(4, d, "tvfc.csv", connectivity_metric="covariance")
+        text = open(os.path.join(d, "tvfc.csv")).read()
+        loaded = SlidingWindows.load_tvfc_estimates(d, "tvfc.csv")
+    open(os.path.join(HERE, "tvfc_reference.csv"), "w").write(text)
+    np.savez_compressed(os.path.join(HERE, "tvfc_csv.npz"), y=y, loaded=np.asarray(loaded, dtype=np.float64))
+    print("csv fixtures written", np.asarray(loaded).shape)
+
+
 def make_wishart():
     import torch
     from oracle import wishart_oracle as wo
@@ -161,9 +179,11 @@ def make_wishart():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wishart", "sliding", "filtering", "summary"]
+    which = sys.argv[1:] or ["wishart", "sliding", "filtering", "summary", "csv"]
     if "summary" in which:
         make_summary()
+    if "csv" in which:
+        make_csv()
     if "wishart" in which:
         make_wishart()
     if "sliding" in which:

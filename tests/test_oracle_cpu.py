@@ -288,3 +288,19 @@ def test_ar1_restatement_is_the_centred_ols_slope():
     y = c[:, 2, 1]; x, z = y[:-1], y[1:]
     slope = ((x - x.mean()) * (z - z.mean())).sum() / ((x - x.mean()) ** 2).sum()
     assert abs(ref[2, 1] - slope) < 1e-12 and ref[1, 2] == ref[2, 1] and ref[0, 0] == 0.0
+
+
+def test_csv_layout_matches_reference_round_trip():
+    """load_tvfc_estimates / to_3d_format on a file the reference's save_tvfc_estimates wrote: same array as the
+    reference's own loader returns (including its leading row-index slice); to_2d_format inverts to_3d_format on
+    symmetric structures."""
+    from fcest_b200.helpers.data import to_2d_format, to_3d_format
+    from fcest_b200.models import SlidingWindows
+    g = np.load(os.path.join(GOLD, "tvfc_csv.npz"))
+    got = SlidingWindows.load_tvfc_estimates(GOLD, "tvfc_reference.csv")
+    assert got.shape == g["loaded"].shape == (13, 3, 3)
+    assert np.array_equal(np.asarray(got, dtype=np.float64), g["loaded"])
+    cov = so.overlapping_windowed_cov(g["y"], 4, 1)
+    assert np.abs(np.asarray(got, dtype=np.float64)[1:] - cov).max() <= 1e-15    # what was saved is the estimate
+    assert np.array_equal(to_3d_format(to_2d_format(cov)), np.swapaxes(cov, 1, 2))
+    assert to_2d_format(cov).shape == (9, 12)

@@ -106,3 +106,19 @@ def test_cv_larger_problem_matches_oracle(cuda):
     assert np.array_equal(np.isinf(got), np.isinf(ref))
     fin = np.isfinite(ref)
     assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-8 * np.abs(ref[fin]))
+
+
+def test_save_and_load_tvfc_estimates_match_reference_file(cuda, tmp_path):
+    """save_tvfc_estimates writes the reference's CSV layout: parsed, it equals the file the reference wrote for
+    the same data (golden fixture) to 1e-12, and load_tvfc_estimates reads our file back."""
+    import pandas as pd
+    from fcest_b200.models import SlidingWindows
+    g = np.load(os.path.join(GOLD, "tvfc_csv.npz"))
+    sw = SlidingWindows(np.linspace(0, 1, 12)[:, None], g["y"])
+    sw.save_tvfc_estimates(4, str(tmp_path / "out"), "tvfc.csv", connectivity_metric="covariance")
+    ours = pd.read_csv(tmp_path / "out" / "tvfc.csv")
+    ref = pd.read_csv(os.path.join(GOLD, "tvfc_reference.csv"))
+    assert list(ours.columns) == list(ref.columns) and ours.shape == ref.shape
+    assert np.abs(ours.to_numpy() - ref.to_numpy()).max() <= 1e-12
+    back = SlidingWindows.load_tvfc_estimates(str(tmp_path / "out"), "tvfc.csv")
+    assert np.abs(np.asarray(back, dtype=np.float64) - g["loaded"]).max() <= 1e-12
