@@ -13,7 +13,7 @@
 // threads = consecutive columns: every load / store of a time step is one coalesced row segment) and the
 // samples of the next FF_AHEAD steps are fetched in one batch ahead of the dependent chain; a software-pipelined
 // variant (next batch in flight during the current one) gained 10 % on one subject and lost 24 % on a
-// 1000-subject batch, which runs at 4.9 TB/s as is (3 fp64 operations per step).
+// 1000-subject batch, which runs at HBM speed as is (3 fp64 operations per step).
 // Every product and sum is rounded separately (__dmul_rn / __dadd_rn, never contracted into FMA) in scipy's
 // order of operations, which makes the result bit-identical to scipy's C loop.
 #include "common.cuh"
@@ -43,50 +43,56 @@ __device__ __forceinline__ double ff_step(const FiltParams& p, double (&z)[FF_MA
   return yn;
 }
 
-// element k of the odd extension of column c (k in [0, N + 2 edge))
-__device__ __forceinline__ double ff_ext(const FiltParams& p, long long c, int k, double x0, double xl) {
-  const int j = k - p.edge;
-  if (j < 0) return __dsub_rn(__dmul_rn(2.0, x0), p.x[(long long)(-j) * p.C + c]);
-  if (j >= p.N) return __dsub_rn(__dmul_rn(2.0, xl), p.x[(long long)(2 * (p.N - 1) - j) * p.C + c]);
-  return p.x[(long long)j * p.C + c];
-}
-
+// The extended signal has three segments -- edge reflected samples, the N samples themselves, edge reflected samples --
+// and each pass walks them in separate loops, so the long middle loop has no branches: batches of FF_AHEAD
+// loads, then FF_AHEAD recurrence steps (and stores).
 template <int ORD>
 __global__ void __launch_bounds__(32) filtfilt_kernel(const __grid_constant__ FiltParams p) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
-  const int L = p.N + 2 * p.edge;
-  const double x0 = p.x[c], xl = p.x[(long long)(p.N - 1) * p.C + c];
+  const int N = p.N, edge = p.edge;
+  const long long C = p.C;
+  const double* x = p.x + c;
+  double* tmp = p.tmp + c;
+  double* out = p.out + c;
+  const double x0 = x[0], xl = x[(long long)(N - 1) * C];
+  const double two_x0 = __dmul_rn(2.0, x0), two_xl = __dmul_rn(2.0, xl);
   double z[FF_MAXORD], buf[FF_AHEAD];
-  // forward pass over the extended signal
-  const double e0 = ff_ext(p, c, 0, x0, xl);
+  // ---- forward pass: tmp[k] = lfilter(ext)[k], zi scaled by ext[0] = 2 x_0 - x_edge
+  {
+    const double e0 = __dsub_rn(two_x0, x[(long long)edge * C]);
 #pragma unroll
-  for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(p.zi[i], e0);
-  double ylast = 0.0;
-  for (int k0 = 0; k0 < L; k0 += FF_AHEAD) {
-#pragma unroll
-    for (int u = 0; u < FF_AHEAD; ++u) buf[u] = (k0 + u < L) ? ff_ext(p, c, k0 + u, x0, xl) : 0.0;
-#pragma unroll
-    for (int u = 0; u < FF_AHEAD; ++u)
-      if (k0 + u < L) {
-        ylast = ff_step<ORD>(p, z, buf[u]);
-        p.tmp[(long long)(k0 + u) * p.C + c] = ylast;
-      }
+    for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(p.zi[i], e0);
   }
-  // backward pass over the reversed forward output (same thread wrote every element it reads)
+  for (int k = 0; k < edge; ++k)
+    tmp[(long long)k * C] = ff_step<ORD>(p, z, __dsub_rn(two_x0, x[(long long)(edge - k) * C]));
+  int j = 0;
+  for (; j + FF_AHEAD <= N; j += FF_AHEAD) {
+#pragma unroll
+    for (int u = 0; u < FF_AHEAD; ++u) buf[u] = x[(long long)(j + u) * C];
+#pragma unroll
+    for (int u = 0; u < FF_AHEAD; ++u) tmp[(long long)(edge + j + u) * C] = ff_step<ORD>(p, z, buf[u]);
+  }
+  for (; j < N; ++j) tmp[(long long)(edge + j) * C] = ff_step<ORD>(p, z, x[(long long)j * C]);
+  double ylast = 0.0;
+  for (int t = 0; t < edge; ++t) {   // ext[N + edge + t] = 2 x_{N-1} - x_{N-2-t}
+    ylast = ff_step<ORD>(p, z, __dsub_rn(two_xl, x[(long long)(N - 2 - t) * C]));
+    tmp[(long long)(edge + N + t) * C] = ylast;
+  }
+  // ---- backward pass over the reversed forward output (this thread wrote every element it reads), zi scaled by
+  //      its last sample; only the middle segment is kept
 #pragma unroll
   for (int i = 0; i < ORD; ++i) z[i] = __dmul_rn(p.zi[i], ylast);
-  for (int k0 = L - 1; k0 >= 0; k0 -= FF_AHEAD) {
+  for (int t = edge - 1; t >= 0; --t) (void)ff_step<ORD>(p, z, tmp[(long long)(edge + N + t) * C]);
+  j = N;
+  for (; j - FF_AHEAD >= 0; j -= FF_AHEAD) {
 #pragma unroll
-    for (int u = 0; u < FF_AHEAD; ++u) buf[u] = (k0 - u >= 0) ? p.tmp[(long long)(k0 - u) * p.C + c] : 0.0;
+    for (int u = 0; u < FF_AHEAD; ++u) buf[u] = tmp[(long long)(edge + j - 1 - u) * C];
 #pragma unroll
-    for (int u = 0; u < FF_AHEAD; ++u)
-      if (k0 - u >= 0) {
-        const double yn = ff_step<ORD>(p, z, buf[u]);
-        const int j = k0 - u - p.edge;
-        if (j >= 0 && j < p.N) p.out[(long long)j * p.C + c] = yn;
-      }
+    for (int u = 0; u < FF_AHEAD; ++u) out[(long long)(j - 1 - u) * C] = ff_step<ORD>(p, z, buf[u]);
   }
+  for (; j > 0; --j) out[(long long)(j - 1) * C] = ff_step<ORD>(p, z, tmp[(long long)(edge + j - 1) * C]);
+  // the leading edge of the reversed pass only feeds samples that are cut off: nothing left to do
 }
 
 template <int ORD>
