@@ -325,6 +325,32 @@ def run_cuda(args):
     except RuntimeError:
         info_ok = False
 
+    # ---- achieved HBM bandwidth of the sliding-window covariance at C3 (outside the timed
+    #      regions; L2 flushed between launches, CUDA events on the launching stream) -------------------------
+    wcov = None
+    if rank == 0 and world == 1:
+        from fcest_b200 import ops as _ops
+        Nw, Dw, Ww = 1200, 100, 30
+        yw = torch.tensor(np.random.default_rng(0).standard_normal((Nw, Dw)), device=dev)
+        ow = torch.empty((Nw, Dw, Dw), dtype=torch.float64, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); _ops.call("fcest_window_cov", _ops.ptr(yw), Nw, Dw, Ww, 1, 0, _ops.ptr(ow)); b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6543.0
+        wbytes = 8.0 * Nw * Dw * Dw + 8.0 * Nw * Dw
+        wms = float(np.median(ts))
+        wcov = {"kernel": "window_cov_bulk_kernel (C3: N=1200 D=100 window_length=30)", "bound": "hbm", "us": wms * 1e3,
+                "algorithmic_bytes": wbytes, "achieved": wbytes / wms * 1e-6, "peak": hbm, "unit": "GB/s",
+                "frac": wbytes / wms * 1e-6 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)"}
+        del yw, ow, flush
+
     if rank == 0:
         peak = json.load(open(FP64_PEAK_FILE))["fp64_tflops"] if os.path.exists(FP64_PEAK_FILE) else 37.0
         lik_ms = per.get("fcest_wishart_loglik", 0.0)
@@ -358,6 +384,7 @@ def run_cuda(args):
                                     "achieved": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12) if lik_ms else None,
                                     "peak": peak, "unit": "TFLOP/s",
                                     "frac": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12 / peak) if lik_ms else None},
+            "roofline_window_cov": wcov,
             "per_call_ms": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
             "elbo_last": last, "cholesky_ok": info_ok,
         }

@@ -15,12 +15,13 @@
 
 namespace fcest {
 
-constexpr int SM_UNROLL = 8;
+constexpr int SM_UNROLL = 32;  // loads in flight per thread: D^2 threads alone (10^4 at D = 100) do not cover the HBM latency
+constexpr int SM_BLOCK = 64;   // small CTAs so that D^2 / 64 of them reach every SM
 
 enum { SUM_MEAN = 0, SUM_VAR = 1, SUM_STD = 2, SUM_ROC = 3, SUM_AR1 = 4 };
 
 template <int METRIC>
-__global__ void __launch_bounds__(128) tvfc_summary_kernel(const double* __restrict__ c, int N, int D,
+__global__ void __launch_bounds__(SM_BLOCK) tvfc_summary_kernel(const double* __restrict__ c, int N, int D,
                                                            double* __restrict__ out) {
   const long long E = (long long)D * D;
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,13 +105,13 @@ extern "C" int fcest_tvfc_summary(const double* cov, int N, int D, int metric, d
   if (N < 1 || !cov || !out) return FCEST_ERR_ARGUMENT;
   if ((metric == SUM_ROC || metric == SUM_AR1) && N < 2) return FCEST_ERR_ARGUMENT;
   const long long E = (long long)D * D;
-  const unsigned grid = (unsigned)((E + 127) / 128);
+  const unsigned grid = (unsigned)((E + SM_BLOCK - 1) / SM_BLOCK);
   switch (metric) {
-    case SUM_MEAN: tvfc_summary_kernel<SUM_MEAN><<<grid, 128, 0, stream>>>(cov, N, D, out); break;
-    case SUM_VAR: tvfc_summary_kernel<SUM_VAR><<<grid, 128, 0, stream>>>(cov, N, D, out); break;
-    case SUM_STD: tvfc_summary_kernel<SUM_STD><<<grid, 128, 0, stream>>>(cov, N, D, out); break;
-    case SUM_ROC: tvfc_summary_kernel<SUM_ROC><<<grid, 128, 0, stream>>>(cov, N, D, out); break;
-    case SUM_AR1: tvfc_summary_kernel<SUM_AR1><<<grid, 128, 0, stream>>>(cov, N, D, out); break;
+    case SUM_MEAN: tvfc_summary_kernel<SUM_MEAN><<<grid, SM_BLOCK, 0, stream>>>(cov, N, D, out); break;
+    case SUM_VAR: tvfc_summary_kernel<SUM_VAR><<<grid, SM_BLOCK, 0, stream>>>(cov, N, D, out); break;
+    case SUM_STD: tvfc_summary_kernel<SUM_STD><<<grid, SM_BLOCK, 0, stream>>>(cov, N, D, out); break;
+    case SUM_ROC: tvfc_summary_kernel<SUM_ROC><<<grid, SM_BLOCK, 0, stream>>>(cov, N, D, out); break;
+    case SUM_AR1: tvfc_summary_kernel<SUM_AR1><<<grid, SM_BLOCK, 0, stream>>>(cov, N, D, out); break;
     default: return FCEST_ERR_ARGUMENT;
   }
   FCEST_CHECK_LAUNCH();
