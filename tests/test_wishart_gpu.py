@@ -406,3 +406,62 @@ def test_fused_q_sqrt_adam_is_bit_identical(cuda):
         assert np.array_equal(u, w)
     iu = np.triu_indices(M, k=1)
     assert not b[1][:, iu[0], iu[1]].any() and not b[2][:, iu[0], iu[1]].any() and not b[3][:, iu[0], iu[1]].any()
+
+
+def test_full_size_properties_c4(cuda):
+    """BASELINE.json's metric configuration (C4: N=1200, D=50, S=8, M=200), where the oracle is too slow to be the
+    checker: size-independent properties instead.
+      1. additivity over time: the ELBO and every gradient of the full evaluation equal the sums over two time
+         halves with the KL term weighted 1/2 each (the identity the time-sharded multi-GPU mode rests on);
+      2. invariance under a permutation of the Monte-Carlo samples (mean over S);
+      3. the analytic gradient against central differences of the forward-only ELBO along random directions in
+         q_mu, q_sqrt, A and lambda (same noise)."""
+    from fcest_b200.models import SparseVariationalWishartProcess
+    N, D, S, M = 1200, 50, 8, 200
+    x, y, _, p = wo.make_inputs(N, D, 1, M=M, seed=0)
+    m = SparseVariationalWishartProcess(D, p["Z"].numpy(), num_mc_samples=S, verbose=False)
+    m.q_mu.assign(p["q_mu"]); m.q_sqrt.assign(p["q_sqrt"])
+    m.likelihood.A_scale_matrix.assign(p["A"]); m.likelihood.additive_part.assign(p["lam"])
+    xd, yd = x.cuda(), y.cuda()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    eps = torch.randn(S, N, D * D, dtype=torch.float64, device="cuda", generator=g)
+    params = [m.q_mu, m.q_sqrt, m.kernel.variance, m.kernel.lengthscales, m.likelihood.A_scale_matrix,
+              m.likelihood.additive_part, m.inducing_variable.Z]
+    full = m.elbo_and_grad((xd, yd), epsilon=eps).item()
+    g_full = [q.grad.clone() for q in params]
+    # 1. two time halves
+    parts, g_sum = 0.0, [torch.zeros_like(t) for t in g_full]
+    for sl in (slice(0, 600), slice(600, N)):
+        parts += m.elbo_and_grad((xd[sl], yd[sl]), epsilon=eps[:, sl].contiguous(), kl_scale=0.5).item()
+        for acc, q in zip(g_sum, params):
+            acc += q.grad
+    assert abs(parts - full) <= 1e-11 * abs(full)
+    for a, b, q in zip(g_sum, g_full, params):
+        if q is m.q_sqrt:
+            # tri_grad takes the whole KL term in every evaluation (the time-sharded mode all-reduces the packed
+            # cotangent before it), so the two halves count d KL / d q_sqrt = tril(L) - diag(1 / L_mm) twice
+            L = torch.tril(m.q_sqrt.unconstrained)
+            kl_grad = L - torch.diag_embed(1.0 / torch.diagonal(L, dim1=-2, dim2=-1))
+            a = a + kl_grad
+        assert _rel(a.cpu().numpy().reshape(-1), b.cpu().numpy().reshape(-1)) < 1e-8, q.name
+    # 2. permutation of the samples
+    perm = torch.tensor([3, 7, 0, 5, 1, 6, 2, 4], device="cuda")
+    e2 = m.elbo((xd, yd), epsilon=eps[perm].contiguous()).item()
+    assert abs(e2 - full) <= 1e-11 * abs(full)
+    # 3. directional derivatives (central differences of the forward-only ELBO, same noise).  The direction leans on
+    #    the gradient itself so that the derivative is large against the rounding of a -4e6 ELBO; q_sqrt moves on
+    #    its strict lower triangle only (its diagonal enters through log L_mm^2 with entries near zero here)
+    rng = np.random.default_rng(2)
+    for q, gq, h in [(m.q_mu, g_full[0], 1e-4), (m.q_sqrt, g_full[1], 1e-5), (m.likelihood.A_scale_matrix, g_full[4], 1e-5),
+                     (m.likelihood.additive_part, g_full[5], 1e-4)]:
+        gdir = torch.tril(gq, diagonal=-1) if q is m.q_sqrt else gq
+        d = gdir / gdir.abs().max() + 0.3 * torch.tensor(rng.standard_normal(tuple(gq.shape)), device="cuda")
+        if q is m.q_sqrt:
+            d = torch.tril(d, diagonal=-1)
+        base = q.unconstrained.clone()
+        q.unconstrained.copy_(base + h * d); ep = m.elbo((xd, yd), epsilon=eps).item()
+        q.unconstrained.copy_(base - h * d); em = m.elbo((xd, yd), epsilon=eps).item()
+        q.unconstrained.copy_(base)
+        fd = (ep - em) / (2 * h)
+        an = float((gq.reshape(-1) * d.reshape(-1)).sum().item())
+        assert abs(fd - an) <= 1e-4 * abs(an), (q.name, fd, an)
