@@ -367,9 +367,10 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel<120,128,40,32,32,3> (3 projection GEMMs per step)",
                          "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three GEMMs,
-                         # from the ncu --set full capture summarised in profiles/r01_ncu_summary.md
-                         "traffic": 759e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 619e6,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three GEMMs
+                         # (969 / 604 / 758 MB for V, Gk, Tk), from the ncu --set full capture of the final round-1
+                         # build summarised in profiles/r01_ncu_summary.md
+                         "traffic": 777e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 619e6,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/FP64_PEAK.json); "
                                         "MEASURED_PEAKS.json has no fp64 figure",
                          "algorithmic_flops_per_launch": flops["projection"] / 3.0,
