@@ -9,6 +9,9 @@
 // so that  V = Pk Sk^T,  dELBO/dSk = g^T Pk  and  T = g Sk  are three *plain* fp64 GEMMs (gemm.cu)
 // with the algorithmic flop count 3 M^2 N R and no recompute.  The kernels in this file are the
 // (cheap) packing / unpacking steps around those GEMMs.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "fcest_b200.h"
 
@@ -416,6 +419,114 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// tri_syrk with the whole factor resident in shared memory (M <= 200, even): the lower 8x8 blocks of L_r
+// (nb (nb + 1) / 2 blocks of 512 bytes, 166 KB at M = 200) are copied in once, then 32 warps compute the output
+// tiles independently -- no k-panels, no block barrier in the main loop, 8 warps per scheduler to cover the LDS /
+// DMMA latencies that bound the output-stationary kernel above (4 warps per scheduler, one barrier per panel).
+// Work unit = a pair of horizontally adjacent tiles (ib, jb0), (ib, jb0 + 1) sharing the A fragment; units are
+// dealt to the warps in descending weight (2 jb0 + 3 block products), serpentine, so the triangular work balances.
+// Block (ib, kb) sits at index ib (ib + 1) / 2 + kb, element (r, c) at r * 8 + (c ^ ((r & 2) << 1)): the fragment
+// pattern [gid][tig + 4h] then touches every bank pair once per half-warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int TSM_WARPS = 32;
+
+__device__ __forceinline__ int tsm_off(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
+
+__global__ void __launch_bounds__(TSM_WARPS * 32, 1)
+tri_syrk_smem_kernel(const double* __restrict__ q_sqrt, int M, double* __restrict__ Sk, long long ldk,
+                     double* __restrict__ klp) {
+  extern __shared__ __align__(16) double Lb[];
+  __shared__ double red[32];
+  const int Mp = (M + 7) / 8 * 8, nb = Mp / 8;
+  const int r_lat = blockIdx.x;
+  const double* __restrict__ L = q_sqrt + (long long)r_lat * M * M;
+  double* __restrict__ out = Sk + (long long)r_lat * ldk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  // ---- copy the lower blocks in: one warp per row, lanes over the 16-byte chunks of columns [0, 8 (ib + 1))
+  for (int i = warp; i < Mp; i += TSM_WARPS) {
+    const int ib = i >> 3, r = i & 7;
+    double* brow = Lb + (size_t)(ib * (ib + 1) / 2) * 64;
+    for (int col = 2 * lane; col < 8 * (ib + 1); col += 64) {
+      const int kb = col >> 3, c = col & 7;
+      // columns <= row (lower triangle) and < M, through the copy size; rows >= M are zero
+      int bytes = (i < M) ? min(M - col, i - col + 1) * 8 : 0;
+      bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      cp_async16(brow + kb * 64 + tsm_off(r, c), bytes > 0 ? L + (long long)i * M + col : L, bytes);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  // KL piece: sum_m log L_mm^2 from the resident diagonal blocks
+  double ld = 0.0;
+  if (tid < M) {
+    const int ib = tid >> 3, r = tid & 7;
+    const double dgl = Lb[(size_t)(ib * (ib + 1) / 2 + ib) * 64 + tsm_off(r, r)];
+    ld = log(dgl * dgl);
+  }
+  // ---- units in descending weight: column pair jb0 = jtop, jtop - 2, ..., 0; rows ib = jb0 .. nb - 1
+  const int fa_off = tsm_off(gid, tig), fb_off = tsm_off(gid, tig + 4);   // [gid][tig], [gid][tig + 4]
+  const long long K = (long long)M * (M + 1) / 2;
+  double tr = 0.0;
+  // unit table (ib << 8 | jb0) in descending weight, built once per CTA; warp w takes entries w, 63 - w, 64 + w, ...
+  __shared__ unsigned short units[13 * 26];
+  const int jtop = (nb - 1) & ~1;
+  int nunits = 0;
+  for (int j = jtop; j >= 0; j -= 2) nunits += nb - j;
+  for (int u = tid; u < nunits; u += blockDim.x) {
+    int j = jtop, rem = u;
+    while (rem >= nb - j) { rem -= nb - j; j -= 2; }
+    units[u] = (unsigned short)(((j + rem) << 8) | j);
+  }
+  __syncthreads();
+  for (int round = 0; round * TSM_WARPS < nunits; ++round) {
+    {
+      const int idx = round * TSM_WARPS + ((round & 1) ? TSM_WARPS - 1 - warp : warp);
+      if (idx >= nunits) continue;
+      const int ib = units[idx] >> 8, jb0 = units[idx] & 255;
+      const bool two = jb0 + 1 <= ib;
+      const double* pa = Lb + (size_t)(ib * (ib + 1) / 2) * 64;
+      const double* pb0 = Lb + (size_t)(jb0 * (jb0 + 1) / 2) * 64;
+      const double* pb1 = Lb + (size_t)((jb0 + 1) * (jb0 + 2) / 2) * 64;
+      double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+      for (int kb = 0; kb <= jb0; ++kb) {   // S[ib][jb] = sum_{kb <= jb} L[ib][kb] L[jb][kb]^T
+        const double a0 = pa[kb * 64 + fa_off], a1 = pa[kb * 64 + fb_off];
+        const double b0 = pb0[kb * 64 + fa_off], b1 = pb0[kb * 64 + fb_off];
+        dmma(c00, c01, a0, b0);
+        dmma(c00, c01, a1, b1);
+        if (two) {
+          const double d0 = pb1[kb * 64 + fa_off], d1 = pb1[kb * 64 + fb_off];
+          dmma(c10, c11, a0, d0);
+          dmma(c10, c11, a1, d1);
+        }
+      }
+      if (two) {   // the second tile also takes kb = jb0 + 1 (its own diagonal block)
+        const int kb = jb0 + 1;
+        dmma(c10, c11, pa[kb * 64 + fa_off], pb1[kb * 64 + fa_off]);
+        dmma(c10, c11, pa[kb * 64 + fb_off], pb1[kb * 64 + fb_off]);
+      }
+      const int row = 8 * ib + gid;
+      if (row < M) {
+        double* orow = out + (long long)row * (row + 1) / 2;
+        const int col0 = 8 * jb0 + 2 * tig;
+        if (col0 <= row) { orow[col0] = c00; if (col0 == row) tr += c00; }
+        if (col0 + 1 <= row) { orow[col0 + 1] = c01; if (col0 + 1 == row) tr += c01; }
+        if (two) {
+          const int col1 = col0 + 8;
+          if (col1 <= row) { orow[col1] = c10; if (col1 == row) tr += c10; }
+          if (col1 + 1 <= row) { orow[col1 + 1] = c11; if (col1 + 1 == row) tr += c11; }
+        }
+      }
+    }
+  }
+  for (long long idx = K + tid; idx < ldk; idx += blockDim.x) out[idx] = 0.0;
+  tr = block_sum(tr, red);
+  ld = block_sum(ld, red);
+  if (tid == 0) { klp[2 * r_lat] = tr; klp[2 * r_lat + 1] = ld; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dP[:, n] (+)= 2 T_n p_n - 2 gs[n] p_n * use_prior,   T_n symmetric from packed Tk[n, idx(i,j)].
 // gs[n] = sum_r g_var[n, r] (row sums, computed here).   grid = N, block = 256, smem = 2M + 32
 // ---------------------------------------------------------------------------------------------
@@ -496,6 +607,18 @@ extern "C" int fcest_pack_outer(const double* P, long long ldp, int M, int N, do
 extern "C" int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* Sk, long long ldk,
                                    double* kl_parts, cudaStream_t stream) {
   if (R <= 0) return 0;
+  // default: the shared-memory-resident kernel (0.70 -> 0.49 ms at C4); FCEST_TRI_SYRK_IMPL=stationary selects the
+  // output-stationary panel kernel
+  static const int use_smem = getenv("FCEST_TRI_SYRK_IMPL") ? strcmp(getenv("FCEST_TRI_SYRK_IMPL"), "stationary") != 0 : 1;
+  if (use_smem && M <= 200 && (M & 1) == 0) {
+    const int nb = (M + 7) / 8;
+    const size_t smem = sizeof(double) * 64 * (size_t)(nb * (nb + 1) / 2);
+    cudaError_t e = cudaFuncSetAttribute(tri_syrk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tri_syrk_smem_kernel<<<R, TSM_WARPS * 32, smem, stream>>>(q_sqrt, M, Sk, ldk, kl_parts);
+    FCEST_CHECK_LAUNCH();
+    return 0;
+  }
   if (M <= 200 && (M & 1) == 0) {
     const int Mp = (M + 7) / 8 * 8;
     const size_t smem = sizeof(double) * 2 * (size_t)Mp * TRI_PITCH;
