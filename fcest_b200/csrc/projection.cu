@@ -527,6 +527,129 @@ tri_syrk_smem_kernel(const double* __restrict__ q_sqrt, int M, double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// tri_grad with the factor resident in shared memory (same layout and occupancy argument as tri_syrk_smem_kernel):
+//   out[ib][jb] = sum_{kb >= jb} Gs[ib][kb] L[kb][jb],   dq_sqrt = tril(out) + kl diag(1 / L_mm)
+// B fragments (L[kb][jb], pattern [tig + 4h][gid]) come from the resident blocks; A fragments (the symmetric unpack of
+// the packed cotangent, diagonal replaced by 2 Gk_ii - kl) are read from global memory with full-sector accesses
+// (rows of 4 / columns of 8 consecutive doubles).  Units (pairs of adjacent tiles of one block row) are handed out in
+// block-row order, so the 32 warps of a CTA work on two or three block rows at a time and the 13 KB of Gs they share
+// stay in L1; the packed cotangent is then read from L2 about once.
+// ---------------------------------------------------------------------------------------------
+template <bool ADAM>
+__global__ void __launch_bounds__(TSM_WARPS * 32, 1)
+tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double* __restrict__ q_sqrt, int M,
+                     double* __restrict__ dq_sqrt, double kl, TriAdam ad) {
+  extern __shared__ __align__(16) double Lb[];
+  __shared__ unsigned short units[13 * 26];
+  __shared__ int next_unit;
+  const int Mp = (M + 7) / 8 * 8, nb = Mp / 8;
+  const int r_lat = blockIdx.x;
+  if (threadIdx.x == 0) next_unit = 0;
+  const double* __restrict__ L = q_sqrt + (long long)r_lat * M * M;
+  const double* __restrict__ G = Gk + (long long)r_lat * ldk;
+  double* __restrict__ dq = dq_sqrt + (long long)r_lat * M * M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  for (int i = warp; i < Mp; i += TSM_WARPS) {   // resident lower blocks of L (see tri_syrk_smem_kernel)
+    const int ib = i >> 3, r = i & 7;
+    double* brow = Lb + (size_t)(ib * (ib + 1) / 2) * 64;
+    for (int col = 2 * lane; col < 8 * (ib + 1); col += 64) {
+      int bytes = (i < M) ? min(M - col, i - col + 1) * 8 : 0;
+      bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+      cp_async16(brow + (col >> 3) * 64 + tsm_off(r, col & 7), bytes > 0 ? L + (long long)i * M + col : L, bytes);
+    }
+  }
+  cp_async_commit();
+  // strict upper triangle of dq_sqrt is zero (under the copy); the fused optimiser never touches it
+  if (!ADAM) {
+    for (int e = tid; e < M * M; e += blockDim.x) {
+      const int i = e / M, j = e - i * M;
+      if (j > i) dq[e] = 0.0;
+    }
+  }
+  // unit table: block rows from the bottom, column pairs left to right (heavy first within a row)
+  int nunits = 0;
+  for (int ib = 0; ib < nb; ++ib) nunits += ib / 2 + 1;
+  for (int u = tid; u < nunits; u += blockDim.x) {
+    int ib = nb - 1, rem = u;
+    while (rem >= ib / 2 + 1) { rem -= ib / 2 + 1; --ib; }
+    units[u] = (unsigned short)((ib << 8) | (2 * rem));
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const int ob0 = tsm_off(tig, gid), ob1 = tsm_off(tig + 4, gid);   // [tig][gid], [tig + 4][gid]
+  // units are handed out in table order from a shared counter: the triangular weights (1 .. 49 block products)
+  // balance dynamically while concurrent warps stay on neighbouring block rows; which warp computes a unit does
+  // not change its result
+  for (;;) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(&next_unit, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= nunits) break;
+    const int ib = units[idx] >> 8, jb0 = units[idx] & 255;
+    const bool two = jb0 + 1 <= ib;
+    const int i = 8 * ib + gid;
+    const bool iok = i < M;
+    const double* Gi = G + (long long)i * (i + 1) / 2;   // packed row i (columns <= i)
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    for (int kb = jb0; kb < nb; ++kb) {
+      // A fragment: Gs[i][k], k = 8 kb + tig (+ 4)
+      const int k0 = 8 * kb + tig, k1 = k0 + 4;
+      double a0 = 0.0, a1 = 0.0;
+      if (kb < ib) {
+        if (iok) { a0 = Gi[k0]; a1 = Gi[k1]; }
+      } else if (kb > ib) {
+        if (iok && k0 < M) a0 = G[(long long)k0 * (k0 + 1) / 2 + i];
+        if (iok && k1 < M) a1 = G[(long long)k1 * (k1 + 1) / 2 + i];
+      } else {
+        if (iok && k0 < M) a0 = (k0 <= i) ? Gi[k0] : G[(long long)k0 * (k0 + 1) / 2 + i];
+        if (iok && k1 < M) a1 = (k1 <= i) ? Gi[k1] : G[(long long)k1 * (k1 + 1) / 2 + i];
+        // out = (Gs + diag(Gk_ii) - kl I) L: the packed diagonal holds W_ii, the KL term is -kl L
+        if (k0 == i) a0 = 2.0 * a0 - kl;
+        if (k1 == i) a1 = 2.0 * a1 - kl;
+      }
+      const double* pb = Lb + (size_t)(kb * (kb + 1) / 2 + jb0) * 64;   // block (kb, jb0); (kb, jb0 + 1) follows
+      dmma(c00, c01, a0, pb[ob0]);
+      dmma(c00, c01, a1, pb[ob1]);
+      if (two && kb > jb0) {
+        dmma(c10, c11, a0, pb[64 + ob0]);
+        dmma(c10, c11, a1, pb[64 + ob1]);
+      }
+    }
+    if (iok) {
+      const long long rbase = (long long)r_lat * M * M + (long long)i * M;
+      const double dinv = kl / Lb[(size_t)(ib * (ib + 1) / 2 + ib) * 64 + tsm_off(gid, gid)];
+      // ADAM: the Keras-Adam update of run_adam applied in place (theta = q_sqrt, all of whose reads went through the
+      // resident copy), else the gradient itself
+      auto emit = [&](int col, double v0, double v1, bool both) {
+        if (ADAM) {
+          double* theta = const_cast<double*>(q_sqrt);
+          const double alpha = ad.alpha_dev[0];
+          for (int e = 0; e < (both ? 2 : 1); ++e) {
+            const long long off = rbase + col + e;
+            double th = theta[off], mi = ad.m[off], vi = ad.v[off];
+            adam_update(th, mi, vi, -(e ? v1 : v0), alpha, ad.b1, ad.b2, ad.eps);
+            ad.m[off] = mi; ad.v[off] = vi; theta[off] = th;
+          }
+        } else if (both) {
+          *reinterpret_cast<double2*>(dq_sqrt + rbase + col) = make_double2(v0, v1);
+        } else {
+          dq_sqrt[rbase + col] = v0;
+        }
+      };
+      const int col0 = 8 * jb0 + 2 * tig;
+      if (col0 + 1 <= i) emit(col0, c00, col0 + 1 == i ? c01 + dinv : c01, true);
+      else if (col0 == i) emit(col0, c00 + dinv, 0.0, false);
+      if (two) {
+        const int col1 = col0 + 8;
+        if (col1 + 1 <= i) emit(col1, c10, col1 + 1 == i ? c11 + dinv : c11, true);
+        else if (col1 == i) emit(col1, c10 + dinv, 0.0, false);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dP[:, n] (+)= 2 T_n p_n - 2 gs[n] p_n * use_prior,   T_n symmetric from packed Tk[n, idx(i,j)].
 // gs[n] = sum_r g_var[n, r] (row sums, computed here).   grid = N, block = 256, smem = 2M + 32
 // ---------------------------------------------------------------------------------------------
@@ -633,9 +756,25 @@ extern "C" int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* S
   return 0;
 }
 
+static int tri_grad_use_smem() {
+  static const int v = getenv("FCEST_TRI_GRAD_IMPL") ? strcmp(getenv("FCEST_TRI_GRAD_IMPL"), "stationary") != 0 : 1;
+  return v;
+}
+
 extern "C" int fcest_tri_grad(const double* Gk, long long ldk, const double* q_sqrt, int R, int M,
                               double* dq_sqrt, double kl, cudaStream_t stream) {
   if (R <= 0) return 0;
+  // default: the shared-memory-resident kernel (1.28 -> 0.97 ms at C4); FCEST_TRI_GRAD_IMPL=stationary selects the
+  // output-stationary panel kernel
+  if (tri_grad_use_smem() && M <= 200 && (M & 1) == 0) {
+    const int nb = (M + 7) / 8;
+    const size_t smem = sizeof(double) * 64 * (size_t)(nb * (nb + 1) / 2);
+    cudaError_t e = cudaFuncSetAttribute(tri_grad_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tri_grad_smem_kernel<false><<<R, TSM_WARPS * 32, smem, stream>>>(Gk, ldk, q_sqrt, M, dq_sqrt, kl, TriAdam());
+    FCEST_CHECK_LAUNCH();
+    return 0;
+  }
   if (M <= 200 && (M & 1) == 0) {
     const int Mp = (M + 7) / 8 * 8;
     const size_t smem = sizeof(double) * 2 * ((size_t)Mp * TRI_PITCH + (size_t)TRI_KP * (Mp + 4));
@@ -656,6 +795,17 @@ extern "C" int fcest_tri_grad_adam(const double* Gk, long long ldk, double* q_sq
   if (R <= 0) return 0;
   if (!Gk || !q_sqrt || !m || !v || !alpha_t) return FCEST_ERR_ARGUMENT;
   if (!(M <= 200 && (M & 1) == 0)) return FCEST_ERR_UNSUPPORTED;   // caller falls back to tri_grad + adam_step
+  if (tri_grad_use_smem()) {
+    const int nb = (M + 7) / 8;
+    const size_t smem_r = sizeof(double) * 64 * (size_t)(nb * (nb + 1) / 2);
+    cudaError_t e2 = cudaFuncSetAttribute(tri_grad_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+    if (e2 != cudaSuccess) return (int)e2;
+    TriAdam ad2;
+    ad2.m = m; ad2.v = v; ad2.alpha_dev = alpha_t; ad2.b1 = b1; ad2.b2 = b2; ad2.eps = eps;
+    tri_grad_smem_kernel<true><<<R, TSM_WARPS * 32, smem_r, stream>>>(Gk, ldk, q_sqrt, M, nullptr, kl, ad2);
+    FCEST_CHECK_LAUNCH();
+    return 0;
+  }
   const int Mp = (M + 7) / 8 * 8;
   const size_t smem = sizeof(double) * 2 * ((size_t)Mp * TRI_PITCH + (size_t)TRI_KP * (Mp + 4));
   cudaError_t e = cudaFuncSetAttribute(tri_stationary_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
