@@ -29,7 +29,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(N=1200, D=50, S=8, M=200)
+WORKLOAD = "C4: SVWP N=1200 D=50 nu=50 S=8 M=200 ELBO+grad"   # identical string in both arms
+METRIC = "Wishart ELBO+grad evals/s (N=1200,D=50,S=8)"
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "FP64_PEAK.json")
+GEMM_KERNEL_NAME = "dgemm_dmma_kernel<120,128,40,32,32,3>"
+LIK_KERNEL_NAME = "wishart_loglik_warp_kernel<7> (+ 2 colsum reductions)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three projection GEMMs, from an ncu --set full
+# capture (a constant from the named profile, NOT measured in the bench run)
+TRAFFIC_BYTES_PER_LAUNCH = 777e6
+TRAFFIC_SOURCE = "constant from profiles/r01_ncu_summary.md (ncu --set full of the round-1 build: 969 / 604 / 758 MB for V, Gk, Tk); not measured in this run"
+CPU_ARM_BUDGET_S = 200.0   # wall-clock budget of the --impl reference run (full-size evaluations only)
 
 
 def algorithmic_flops(N, D, S, M):
@@ -46,47 +55,68 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference's TF/GPflow path, timed on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_eval_seconds(n_time, reps, warm):
+def host_threads() -> int:
+    """All the host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the thread
+    count is pinned explicitly instead of being inherited from the launcher."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_inputs():
     from oracle import wishart_oracle as wo
-    x, y, eps, p = wo.make_inputs(CFG["N"], CFG["D"], CFG["S"], M=CFG["M"], seed=0)
-    x, y, eps = x[:n_time], y[:n_time], eps[:, :n_time]
-    times = []
-    for i in range(warm + reps):
-        t0 = time.perf_counter()
-        wo.svgp_elbo_and_grad_chunked(p, x, y, eps, chunk=125)
-        dt = time.perf_counter() - t0
-        if i >= warm:
-            times.append(dt)
-    return times
+    return wo.make_inputs(CFG["N"], CFG["D"], CFG["S"], M=CFG["M"], seed=0)
+
+
+def cpu_eval(inputs):
+    """ONE full-size C4 evaluation (ELBO + gradient w.r.t. every trainable) of the CPU restatement; returns
+    (seconds, elbo, grads).  Never a sub-sample of the time axis."""
+    from oracle import wishart_oracle as wo
+    x, y, eps, p = inputs
+    t0 = time.perf_counter()
+    elbo, g = wo.svgp_elbo_and_grad_chunked(p, x, y, eps, chunk=125)
+    return time.perf_counter() - t0, elbo, g
+
+
+CPU_SAMPLE = ("full C4 evaluations (N=1200, D=50, S=8, M=200; ELBO + gradient of every trainable) of the torch-CPU "
+              "float64 restatement of the reference's TF/GPflow op sequence (oracle/wishart_oracle.py, LTA "
+              "materialised 125 latents at a time); not TensorFlow")
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    threads = torch.get_num_threads()
-    N = CFG["N"]
-    # calibrate: one full-size evaluation; shrink the per-step sample if K steps would take too long
-    t_full = cpu_eval_seconds(N, 1, 0)[0]
-    n_sub, ratio = N, 1.0
-    if t_full * (args.steps + args.warmup) > 240.0:
-        n_sub = N // 8
-        t_sub = min(cpu_eval_seconds(n_sub, 2, 0))
-        ratio = t_full / t_sub  # measured cost ratio full / sample (not assumed linear)
-    times = cpu_eval_seconds(n_sub, args.steps, args.warmup)
-    t_step = float(np.mean(times)) * ratio
+    threads = host_threads()
+    inputs = cpu_inputs()
+    t_start = time.perf_counter()
+    # warm-up: at least one full evaluation; more (up to --warmup) only while they fit a quarter of the budget
+    warm_times = [cpu_eval(inputs)[0]]
+    while len(warm_times) < args.warmup and (len(warm_times) + 1) * max(warm_times) < 0.25 * CPU_ARM_BUDGET_S:
+        warm_times.append(cpu_eval(inputs)[0])
+    # timed steps: full evaluations; the step COUNT shrinks if K of them would not fit the budget
+    left = CPU_ARM_BUDGET_S - (time.perf_counter() - t_start)
+    steps = int(max(1, min(args.steps, left // max(min(warm_times), 1e-3))))
+    times = [cpu_eval(inputs)[0] for _ in range(steps)]
+    t_step = float(np.mean(times))
     value = 1.0 / t_step
-    sample = (f"full C4 evaluation per step (N={N}, D=50, S=8, M=200), torch-CPU float64 restatement of the "
-              f"TF/GPflow op sequence, LTA materialised 125 latents at a time") if n_sub == N else (
-        f"{n_sub} of {N} time points per step, scaled by the measured full/sample cost ratio {ratio:.2f}")
     line = {
-        "impl": "reference", "metric": "Wishart ELBO+grad evals/s (N=1200,D=50,S=8)", "value": value,
-        "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": value,
+        "unit": "evals/s", "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps,
+        "warmup": len(warm_times), "warmup_requested": args.warmup,
         "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4: SVWP N=1200 D=50 nu=50 S=8 M=200 ELBO+grad", "note": "restatement, not TensorFlow"},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD,
+                   "note": "CPU restatement of the reference path on the host cores (rank 0 only); not TensorFlow; "
+                           "every timed step is a full-size evaluation, the step count is cut to fit "
+                           f"{CPU_ARM_BUDGET_S:.0f} s of wall clock"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} timed + {len(warm_times)} warm-up " + CPU_SAMPLE},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
@@ -95,17 +125,82 @@ def run_reference(args):
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
 def build_model(seed, device):
+    from fcest_b200.helpers.synthetic import make_synthetic
     from fcest_b200.models import SparseVariationalWishartProcess
-    from oracle import wishart_oracle as wo  # input generator only (synthetic data + perturbed parameters)
-    x, y, _, p = wo.make_inputs(CFG["N"], CFG["D"], 1, M=CFG["M"], seed=seed)
-    m = SparseVariationalWishartProcess(CFG["D"], p["Z"].numpy(), num_mc_samples=CFG["S"], verbose=False,
+    p = make_synthetic(CFG["N"], CFG["D"], CFG["S"], M=CFG["M"], seed=seed, want_eps=False)
+    m = SparseVariationalWishartProcess(CFG["D"], p["Z"], num_mc_samples=CFG["S"], verbose=False,
                                         device=device)
     m.q_mu.assign(p["q_mu"])
     m.q_sqrt.assign(p["q_sqrt"])
     m.likelihood.A_scale_matrix.assign(p["A"])
     m.likelihood.additive_part.assign(p["lam"])
     m.likelihood.seed(1234 + seed)
-    return m, x.numpy(), y.numpy()
+    return m, p["x"], p["y"]
+
+
+def measure_fp64_peak(dev):
+    """cuBLAS DGEMM 8192^3 through torch.matmul (2 N^3 flop), best of 10 after 2 warm-up calls, CUDA events: the
+    fp64 roofline denominator, measured in this run on this GPU (MEASURED_PEAKS.json carries no fp64 figure)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    best = float("inf")
+    for i in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) * 1e-12
+
+
+def strong_scaling_block(dev, rank, world, K, single_gpu_ms):
+    """ONE C4 subject over all ranks (LatentShardedSVWP: conditional sharded by latent GP, likelihood by time, two
+    all-to-alls + one small all-reduce per evaluation): parity against the unsharded evaluation on the same noise,
+    then K timed evaluations (barrier + device events, max over ranks)."""
+    import torch.distributed as dist
+    from fcest_b200 import ops
+    from fcest_b200.parallel import LatentShardedSVWP
+    m, x_np, y_np = build_model(seed=0, device=dev)       # the same subject on every rank
+    xd, yd = torch.tensor(x_np, device=dev), torch.tensor(y_np, device=dev)
+    N, D, S = CFG["N"], CFG["D"], CFG["S"]
+    eps = torch.empty((S, N, D * D), dtype=torch.float64, device=dev)
+    ops.randn(eps, 4242, 0)                               # counter-based: identical on every rank
+    params = {"q_mu": m.q_mu, "q_sqrt": m.q_sqrt, "kvar": m.kernel.variance, "kls": m.kernel.lengthscales,
+              "A": m.likelihood.A_scale_matrix, "lam": m.likelihood.additive_part, "Z": m.inducing_variable.Z}
+    ref_elbo = m.elbo_and_grad((xd, yd), epsilon=eps).item()
+    ref = {k: q.grad.clone() for k, q in params.items()}
+    sh = LatentShardedSVWP(m)
+    elbo = sh.elbo_and_grad((xd, yd), epsilon=eps).item()
+    lat = sh.latents
+    errs = {"elbo": abs(elbo - ref_elbo) / abs(ref_elbo),
+            "q_mu": float((sh.q_mu_grad_local - ref["q_mu"][:, lat]).abs().max() / ref["q_mu"].abs().max()),
+            "q_sqrt": float((sh.q_sqrt_grad_local - ref["q_sqrt"][lat]).abs().max() / ref["q_sqrt"].abs().max())}
+    for k in ("kvar", "kls", "A", "lam", "Z"):
+        errs[k] = float((params[k].grad - ref[k]).abs().max() / ref[k].abs().max())
+    e = torch.tensor([max(errs.values())], dtype=torch.float64, device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    del ref
+    for _ in range(5):
+        sh.elbo_and_grad((xd, yd), check=False)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        sh.elbo_and_grad((xd, yd), check=False)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    return {"what": "ONE C4 subject sharded over all GPUs (LatentShardedSVWP: conditional by latent GP, likelihood by "
+                    "time block; strong scaling)", "n_gpus": world, "ms_per_step": ms, "evals_per_s": 1e3 / ms,
+            "single_gpu_ms_per_step": single_gpu_ms, "speedup_vs_1gpu": single_gpu_ms / ms,
+            "alltoall_bytes_per_step": int(2 * 2 * 8 * N * D * D), "allreduce_bytes_per_step": int(8 * (3 + D * D + D + CFG["M"])),
+            "max_rel_err_vs_unsharded": float(e.item()), "rel_err_rank0": errs, "steps": K,
+            "timing": "barrier + CUDA events on the launching stream, max over ranks"}
 
 
 class ClockSampler:
@@ -251,7 +346,8 @@ def run_cuda(args):
     sampler = ClockSampler(local) if rank == 0 else None   # NVML attach happens here, outside the timed region
     # at least W steps, and at least 24 (~0.4 s of load at C4: clock ramp, allocator, lazy module loads); a fixed
     # count so that every rank issues the same number of collectives
-    for _ in range(max(W, 24)):
+    warm_steps = max(W, 24)
+    for _ in range(warm_steps):
         step((x_dev, y_dev))
     barrier()
 
@@ -351,28 +447,37 @@ def run_cuda(args):
                 "frac": wbytes / wms * 1e-6 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)"}
         del yw, ow, flush
 
+    # ---- fp64 roofline denominator measured in this run; strong-scaling leg (N > 1) ----------------------------
+    peak_measured = measure_fp64_peak(dev) if rank == 0 else None
+    del model
+    torch.cuda.empty_cache()
+    strong = strong_scaling_block(dev, rank, world, K, t_ms / K) if world > 1 else None
+
     if rank == 0:
-        peak = json.load(open(FP64_PEAK_FILE))["fp64_tflops"] if os.path.exists(FP64_PEAK_FILE) else 37.0
+        peak_file = json.load(open(FP64_PEAK_FILE))["fp64_tflops"] if os.path.exists(FP64_PEAK_FILE) else None
+        peak = peak_measured
         lik_ms = per.get("fcest_wishart_loglik", 0.0)
         line = {
-            "metric": "Wishart ELBO+grad evals/s (N=1200,D=50,S=8)", "value": value, "unit": "evals/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": K, "warmup": warm_steps, "warmup_requested": args.warmup,
+            "ms_per_step": t_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4: SVWP N=1200 D=50 nu=50 S=8 M=200 ELBO+grad, one subject per GPU",
+            "config": {"workload": WORKLOAD,
+                       "sharding": "one independent C4 subject per GPU (replicas; ELBO sum all-reduced)",
                        "l2": "per-step working set 2.8 GB (q_sqrt, Sk, Pk, Gk, Tk, eps) >> 126 MB L2, no flush needed",
                        "rng": "fresh Philox N(0,1) draw per step, generated on device inside the step"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_pin.numel() * 8 + y_pin.numel() * 8),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel<120,128,40,32,32,3> (3 projection GEMMs per step)",
+            "roofline": {"bound": "tensor", "kernel": GEMM_KERNEL_NAME + " (3 projection GEMMs per step)",
                          "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three GEMMs
-                         # (969 / 604 / 758 MB for V, Gk, Tk), from the ncu --set full capture of the final round-1
-                         # build summarised in profiles/r01_ncu_summary.md
-                         "traffic": 777e6, "traffic_unit": "bytes/launch", "algorithmic_bytes_per_launch": 619e6,
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/FP64_PEAK.json); "
-                                        "MEASURED_PEAKS.json has no fp64 figure",
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch",
+                         "traffic_source": TRAFFIC_SOURCE,
+                         "algorithmic_bytes_per_launch": 619e6,
+                         "peak_source": "measured in THIS run on this GPU: cuBLAS DGEMM 8192^3 via torch.matmul, best of "
+                                        "10, CUDA events (MEASURED_PEAKS.json has no fp64 figure)",
+                         "peak_builder_file": peak_file,
                          "algorithmic_flops_per_launch": flops["projection"] / 3.0,
                          "launches_timed": len(gemm_ms),
                          "how": "CUDA events around every projection GEMM launch in a separate pass of the same K steps "
@@ -381,7 +486,7 @@ def run_cuda(args):
             "roofline_step": {"algorithmic_flops": sum(flops.values()),
                               "achieved": sum(flops.values()) / (t_ms / K * 1e-3) * 1e-12, "peak": peak,
                               "unit": "TFLOP/s", "frac": sum(flops.values()) / (t_ms / K * 1e-3) * 1e-12 / peak},
-            "roofline_likelihood": {"kernel": "wishart_loglik_warp_kernel<7> (+ 2 colsum reductions)", "ms": lik_ms,
+            "roofline_likelihood": {"kernel": LIK_KERNEL_NAME, "ms": lik_ms,
                                     "achieved": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12) if lik_ms else None,
                                     "peak": peak, "unit": "TFLOP/s",
                                     "frac": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12 / peak) if lik_ms else None},
@@ -389,13 +494,33 @@ def run_cuda(args):
             "per_call_ms": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
             "elbo_last": last, "cholesky_ok": info_ok,
         }
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            threads = torch.get_num_threads()
-            ts = cpu_eval_seconds(CFG["N"], 2, 1)
+            # CPU baseline + parity at the metric's own configuration: the SAME epsilon goes through the CPU
+            # restatement and through the CUDA path (fresh model at the same seed), ELBO and every gradient compared
+            threads = host_threads()
+            inputs = cpu_inputs()
+            runs = [cpu_eval(inputs) for _ in range(3)]
+            ts = [r[0] for r in runs[1:]]
+            _, elbo_ref, g_ref = runs[-1]
             line["cpu_baseline"] = {
                 "value": 1.0 / min(ts), "unit": "evals/s", "cores": threads, "kind": "port",
-                "sample": "3 full C4 evaluations (1 warm-up, best of 2) of the torch-CPU float64 restatement of the "
-                          "reference's TF/GPflow op sequence (oracle/wishart_oracle.py); not TensorFlow"}
+                "sample": "best of 2 after 1 warm-up: " + CPU_SAMPLE}
+            m2, x_np2, y_np2 = build_model(seed=0, device=dev)
+            eps_dev = inputs[2].to(dev)
+            elbo_cuda = m2.elbo_and_grad((torch.tensor(x_np2, device=dev), torch.tensor(y_np2, device=dev)),
+                                         epsilon=eps_dev).item()
+            got = {"q_mu": m2.q_mu.grad, "q_sqrt": m2.q_sqrt.grad, "A": m2.likelihood.A_scale_matrix.grad,
+                   "lam": m2.likelihood.additive_part.grad, "u_var": m2.kernel.variance.grad,
+                   "u_ls": m2.kernel.lengthscales.grad, "Z": m2.inducing_variable.Z.grad}
+            grel = {k: float((v.cpu().reshape(-1) - g_ref[k].reshape(-1)).abs().max() / g_ref[k].abs().max())
+                    for k, v in got.items()}
+            line["parity_c4"] = {"elbo_rel": abs(elbo_cuda - elbo_ref) / abs(elbo_ref), "grad_rel_max": max(grel.values()),
+                                 "grad_rel": grel, "elbo_cuda": elbo_cuda, "elbo_cpu": elbo_ref,
+                                 "against": "oracle/wishart_oracle.py (pinned to the reference's own likelihood source, "
+                                            "tests/golden/wishart_reference.npz) on the same epsilon, full C4 size",
+                                 "tolerance": {"elbo_rel": 1e-8, "grad_rel_max": 1e-7}}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -88,16 +88,22 @@ def require_cuda() -> None:
         raise RuntimeError("fcest_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
 
 
+_arg_device = None   # device of the tensors marshalled for the next call()
+
+
 def ptr(t):
-    """Device pointer of a tensor (or NULL)."""
+    """Device pointer of a tensor (or NULL).  Also notes the tensor's device: ``call`` launches on THAT device's
+    current stream, not on whatever device happens to be current in the calling thread."""
+    global _arg_device
     if t is None:
         return None
     assert t.is_cuda and t.dtype in (torch.float64, torch.int32), (t.device, t.dtype)
+    _arg_device = t.device   # every operand of one call lives on one device (the kernels take raw pointers)
     return C.c_void_p(t.data_ptr())
 
 
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 _ERR = {-1: "operand alignment (16-byte pointers, even leading dimensions)", -2: "unsupported size",
@@ -111,18 +117,27 @@ PROFILE = None
 
 def call(name: str, *args, flops: float = 0.0):
     """Invoke an ``int``-returning entry point on the current stream and raise on a non-zero status."""
+    global _arg_device
     require_cuda()
     fn = getattr(load_library(), name)
+    dev, _arg_device = _arg_device, None
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):   # kernels launch in the context of the device that owns the operands
+            return _launch(fn, name, args, flops, dev)
+    return _launch(fn, name, args, flops, dev)
+
+
+def _launch(fn, name, args, flops, dev):
     prof = PROFILE
     if prof is not None and flops >= prof["min_flops"]:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        rc = fn(*args, stream())
-        ev1.record()
+        ev0.record(torch.cuda.current_stream(dev))
+        rc = fn(*args, stream(dev))
+        ev1.record(torch.cuda.current_stream(dev))
         prof["records"].append((name, flops, ev0, ev1))
     else:
-        rc = fn(*args, stream())
+        rc = fn(*args, stream(dev))
     if rc != 0:
         what = _ERR.get(rc, f"CUDA error {rc}")
         raise RuntimeError(f"{name} failed: {what}")

@@ -48,7 +48,7 @@ def are_all_positive_definite(covariance_matrices) -> bool:
         t = torch.as_tensor(np.asarray(t), dtype=torch.float64)
     if t.dim() == 2:
         t = t[None]
-    t = t.to(device="cuda", dtype=torch.float64).contiguous()
+    t = t.to(device=t.device if t.is_cuda else "cuda", dtype=torch.float64).contiguous()
     B, D = t.shape[0], t.shape[-1]
     info = torch.zeros(B, dtype=torch.int32, device=t.device)
     scratch = None

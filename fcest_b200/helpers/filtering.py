@@ -97,7 +97,7 @@ def _filtfilt_columns(b: np.ndarray, a: np.ndarray, data):
         x = x[:, None]
     if x.dim() != 2:
         raise ValueError("expected a (N,) series or a (N, C) array")
-    x = x.to(device="cuda", dtype=torch.float64).contiguous()
+    x = x.to(device=x.device if x.is_cuda else "cuda", dtype=torch.float64).contiguous()
     n, c = x.shape
     order = len(a) - 1
     padlen = 3 * max(len(a), len(b))

@@ -31,7 +31,7 @@ def _summary(full_covariance_structure, metric: str):
         np.ascontiguousarray(full_covariance_structure, dtype=np.float64))
     if c.dim() != 3 or c.shape[1] != c.shape[2]:
         raise ValueError("expected a TVFC array of shape (N, D, D)")
-    c = c.to(device="cuda", dtype=torch.float64).contiguous()
+    c = c.to(device=c.device if c.is_cuda else "cuda", dtype=torch.float64).contiguous()
     n, d = c.shape[0], c.shape[1]
     out = torch.empty((d, d), dtype=torch.float64, device=c.device)
     ops.call("fcest_tvfc_summary", ops.ptr(c), n, d, _METRIC[metric], ops.ptr(out))

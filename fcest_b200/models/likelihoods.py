@@ -109,6 +109,7 @@ class WishartProcessLikelihood(MonteCarloLikelihood):
         out = ops.wishart_loglik(f_mean, f_variance, epsilon, y_data, self.A_scale_matrix.unconstrained,
                                  self.additive_part.unconstrained, need_grad=need_grad)
         out["epsilon"] = epsilon
+        self._last_info = out["info"]   # Cholesky status of this call (0 = ok), for callers that only take ve
         return out if need_grad else out["ve"]
 
     def check_info(self, info: torch.Tensor) -> None:

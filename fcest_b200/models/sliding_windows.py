@@ -96,7 +96,7 @@ class SlidingWindows:
             cls._pinned = torch.empty(t.numel(), dtype=torch.float64, pin_memory=True)
         stage = cls._pinned[:t.numel()].view(t.shape)
         stage.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(t.device).synchronize()
         # pinned staging -> caller-owned pageable memory with torch's multi-threaded copy (numpy's single-threaded
         # .copy() of the 96 MB result cost more than the kernel and the PCIe transfer together)
         return torch.empty(t.shape, dtype=torch.float64).copy_(stage).numpy()

@@ -102,11 +102,15 @@ class _WishartProcessBase:
         return cond.conditional_forward(self.kernel, x, x, self.q_mu.unconstrained,
                                         self.q_sqrt.unconstrained, vgp=True, want_kl=want_kl)
 
-    def elbo(self, data=None, epsilon=None) -> torch.Tensor:
-        """Evidence lower bound (device scalar): sum_n var_exp[n] - KL  (gpflow SVGP.elbo / VGP.elbo)."""
+    def elbo(self, data=None, epsilon=None, check: bool = True) -> torch.Tensor:
+        """Evidence lower bound (device scalar): sum_n var_exp[n] - KL  (gpflow SVGP.elbo / VGP.elbo).
+        A failed Cholesky (kernel matrix or a Sigma) raises, as ``tf.linalg.cholesky`` does in the reference."""
         x, y = self._data(data)
         fmean, fvar, kl, st = self._moments(x)
         ve = self.likelihood.variational_expectations(x, fmean, fvar, y, epsilon=epsilon)
+        if check:
+            self._check_chol(st.info)
+            self.likelihood.check_info(self.likelihood._last_info)
         out = torch.empty(1, dtype=F64, device=self.device)
         ops.sum_into(ve, ve.numel(), 1, 1.0, out, False)
         ops.axpby(-1.0, kl, 1.0, out)

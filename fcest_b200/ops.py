@@ -39,12 +39,15 @@ def ld(t: torch.Tensor) -> int:
 
 
 _ws_cache: dict = {}
+_ws_retired: list = []   # outgrown scratch buffers stay alive: a captured CUDA graph may hold their raw pointers
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
     key = (str(device), torch.cuda.current_stream(device).cuda_stream)  # one scratch buffer per stream
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() * 8 < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)   # never hand memory a graph replay still writes back to the allocator
         buf = torch.empty((max(nbytes, 1 << 20) + 7) // 8, dtype=F64, device=device)
         _ws_cache[key] = buf
     return buf

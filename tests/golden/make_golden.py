@@ -10,9 +10,13 @@
   metrics that need no statsmodels (mean, variance, std, rate_of_change).
 * tvfc_reference.csv / tvfc_csv.npz -- a file written by the REFERENCE's SlidingWindows.save_tvfc_estimates and
   what its load_tvfc_estimates reads back from it.
-* wishart_*.npz -- outputs of the CPU oracle (oracle/wishart_oracle.py).  TensorFlow / GPflow cannot be
-  installed here, so these pin the *restatement* (regression fixtures), not the reference: "parity
-  unpinned" for the Wishart path, as stated in the oracle header and DESIGN.md.
+* wishart_reference.npz, svwp_reference_params.json, vwp_reference_params.json -- outputs of the REFERENCE's own
+  source text for the FCEst-owned arithmetic of the Wishart path (likelihoods.py, wishart_process.py,
+  array_operations.py), executed on the NumPy-backed tensorflow stand-in tests/golden/tf_numpy_shim.py with the
+  N(0,1) draws injected.  These pin oracle/wishart_oracle.py (and the CUDA path) to the reference's code for
+  everything FCEst itself computes; the GPflow formulas (conditional, KL, Matern52, Adam) stay a restatement.
+* wishart_oracle.npz -- outputs of the CPU oracle (oracle/wishart_oracle.py) for the full ELBO + gradient
+  (regression fixtures of the restatement, GPflow part included).
 """
 import os
 import sys
@@ -90,6 +94,22 @@ def make_sliding():
     cv["bounds_1200"] = np.array([sw.minimum_proposal_window_length, sw.maximum_proposal_window_length])
     np.savez_compressed(os.path.join(HERE, "sliding_cv.npz"), **cv)
     print("sliding fixtures written")
+
+
+def make_sliding_c3():
+    """BASELINE.json config 3 (N=1200, D=100, window_length=30 + CV window search) run through the REFERENCE
+    itself (about three minutes: 81 520 eigendecompositions and a DataFrame that grows cell by cell)."""
+    SlidingWindows = import_reference_sliding_windows()
+    y = np.random.default_rng(0).standard_normal((1200, 100))
+    sw = SlidingWindows(np.linspace(0, 1, 1200)[:, None], y)
+    cov = sw.overlapping_windowed_cov_estimation(30)
+    rows = np.array([0, 15, 600, 1199])
+    df = sw.find_cross_validated_optimal_window_length()
+    np.savez_compressed(os.path.join(HERE, "sliding_c3.npz"), seed=np.array(0), rows=rows, cov_rows=cov[rows],
+                        cov_checksum=np.array([cov.sum(), np.abs(cov).sum(), (cov * cov).sum()]),
+                        table=df.to_numpy(dtype=np.float64), locs=df.index.to_numpy(), windows=df.columns.to_numpy(),
+                        best=np.array(sw.get_optimal_window_length(df)))
+    print("C3 sliding fixtures written; best window", sw.get_optimal_window_length(df))
 
 
 def make_filtering():
@@ -178,8 +198,198 @@ def make_wishart():
     print("wishart fixtures written")
 
 
+def make_wishart_reference():
+    """Run the reference's own likelihood / prediction / checkpoint source on the NumPy tensorflow stand-in."""
+    import json
+    import tempfile
+    sys.path.insert(0, HERE)
+    import tf_numpy_shim as shim
+    tf = shim.install()
+    for name in [k for k in sys.modules if k == "fcest" or k.startswith("fcest.")]:
+        del sys.modules[name]   # a stub-imported copy (sliding fixtures) must not be reused
+    from fcest.models.likelihoods import WishartProcessLikelihood
+    from fcest.models.wishart_process import SparseVariationalWishartProcess, VariationalWishartProcess
+    from fcest.helpers.array_operations import are_all_positive_definite, convert_tensor_to_correlation
+    import io
+    import contextlib
+
+    rng = np.random.default_rng(77)
+    out = {}
+    # (tag, N, D, S, A option, perturb the parameters away from their initial values)
+    lik_cases = [("full", 12, 5, 3, "train_full_matrix", True), ("ident", 10, 4, 2, "identity", True),
+                 ("scaled", 9, 6, 4, "scaled", True), ("diag", 11, 3, 5, "train_diagonal", True),
+                 ("init", 8, 4, 3, "train_full_matrix", False), ("d1", 7, 1, 2, "train_full_matrix", True),
+                 ("d17", 6, 17, 2, "train_full_matrix", True), ("c1", 200, 3, 5, "train_full_matrix", True),
+                 ("d50", 3, 50, 8, "train_full_matrix", True), ("d60", 2, 60, 2, "train_diagonal", True)]
+    tags = []
+    for tag, N, D, S, option, perturb in lik_cases:
+        with contextlib.redirect_stdout(io.StringIO()):
+            lik = WishartProcessLikelihood(D=D, num_mc_samples=S, A_scale_matrix_option=option,
+                                           train_additive_noise=True, verbose=True)
+        out[f"lik_{tag}_A_init"] = lik.A_scale_matrix.numpy().copy()
+        out[f"lik_{tag}_lam_init"] = lik.additive_part.numpy().copy()
+        out[f"lik_{tag}_dims"] = np.array([lik.input_dim, lik.latent_dim, lik.observation_dim, lik.D, lik.nu,
+                                           int(lik.A_scale_matrix.trainable), int(lik.additive_part.trainable)])
+        if perturb:
+            if option in ("train_full_matrix", "train_diagonal"):
+                lik.A_scale_matrix.assign(lik.A_scale_matrix.numpy() + 0.1 * rng.standard_normal(lik.A_scale_matrix.shape))
+            lik.additive_part.assign(lik.additive_part.numpy() + 0.3 * rng.standard_normal(D))
+        R = D * D
+        x = np.linspace(0, 1, N)[:, None]
+        y = rng.standard_normal((N, D))
+        f_mean = 0.5 * rng.standard_normal((N, R))
+        f_var = 0.05 + rng.random((N, R))
+        eps = rng.standard_normal((S, N, R))
+        shim.push_normal(eps)
+        ve = lik.variational_expectations(x, tf.constant(f_mean), tf.constant(f_var), y)
+        f_sample = rng.standard_normal((S, N, D, D))
+        lp = lik._log_prob(x, tf.constant(f_sample), y)
+        cov = rng.standard_normal((2, D, D))
+        out[f"lik_{tag}_A"] = lik.A_scale_matrix.numpy().copy()
+        out[f"lik_{tag}_lam"] = lik.additive_part.numpy().copy()
+        out[f"lik_{tag}_y"] = y
+        out[f"lik_{tag}_f_mean"] = f_mean
+        out[f"lik_{tag}_f_var"] = f_var
+        out[f"lik_{tag}_eps"] = eps
+        out[f"lik_{tag}_ve"] = ve.numpy()
+        out[f"lik_{tag}_f_sample"] = f_sample
+        out[f"lik_{tag}_log_prob"] = lp.numpy()
+        out[f"lik_{tag}_cov_in"] = cov
+        out[f"lik_{tag}_cov_noise"] = lik._add_diagonal_additive_noise(tf.constant(cov)).numpy()
+        tags.append(f"{tag}:{option}")
+    out["lik_cases"] = np.array(tags)
+    try:
+        WishartProcessLikelihood(D=4, nu=3)
+        raise AssertionError("nu < D must raise")
+    except Exception as e:
+        out["nu_lt_D_message"] = np.array(str(e))
+
+    # prediction: the reference's predict_cov / predict_corr / _get_cov_samples run on a model object whose
+    # predict_f (GPflow's) returns a prescribed (mean, variance) pair
+    ptags = []
+    for tag, cls, N, D, S, option in [("vwp", VariationalWishartProcess, 6, 3, 7, "train_full_matrix"),
+                                      ("svwp", SparseVariationalWishartProcess, 5, 4, 9, "train_full_matrix"),
+                                      ("svwp_diag", SparseVariationalWishartProcess, 4, 9, 6, "train_diagonal"),
+                                      ("vwp_scaled", VariationalWishartProcess, 3, 18, 5, "scaled")]:
+        model = object.__new__(cls)
+        model.D, model.nu = D, D
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.likelihood = WishartProcessLikelihood(D=D, num_mc_samples=2, A_scale_matrix_option=option,
+                                                        train_additive_noise=True, verbose=False)
+        lik = model.likelihood
+        if option in ("train_full_matrix", "train_diagonal"):
+            lik.A_scale_matrix.assign(lik.A_scale_matrix.numpy() + 0.1 * rng.standard_normal(lik.A_scale_matrix.shape))
+        lik.additive_part.assign(lik.additive_part.numpy() + 0.3 * rng.standard_normal(D))
+        f_mean = 0.7 * rng.standard_normal((N, D * D))
+        f_var = 0.05 + rng.random((N, D * D))
+        model.predict_f = lambda x_new, fm=f_mean, fv=f_var: (tf.constant(fm), tf.constant(fv))
+        x_new = np.linspace(0, 1, N)[:, None]
+        eps = rng.standard_normal((S, N, D, D))
+        shim.push_normal(eps)
+        samples = model._get_cov_samples(x_new, S)
+        shim.push_normal(eps)
+        cov_mean, cov_std = model.predict_cov(x_new, S)
+        shim.push_normal(eps)
+        corr_mean, corr_std = model.predict_corr(x_new, S)
+        if cls is SparseVariationalWishartProcess:
+            shim.push_normal(eps)
+            assert np.array_equal(model.predict_cov_samples(x_new, S).numpy(), samples.numpy())
+        out[f"pred_{tag}_A"] = lik.A_scale_matrix.numpy().copy()
+        out[f"pred_{tag}_lam"] = lik.additive_part.numpy().copy()
+        out[f"pred_{tag}_f_mean"] = f_mean
+        out[f"pred_{tag}_f_var"] = f_var
+        out[f"pred_{tag}_eps"] = eps
+        out[f"pred_{tag}_samples"] = samples.numpy()
+        out[f"pred_{tag}_cov_mean"] = cov_mean.numpy()
+        out[f"pred_{tag}_cov_std"] = cov_std.numpy()
+        out[f"pred_{tag}_corr_mean"] = corr_mean.numpy()
+        out[f"pred_{tag}_corr_std"] = corr_std.numpy()
+        out[f"pred_{tag}_corr_samples"] = convert_tensor_to_correlation(samples).numpy()
+        ptags.append(f"{tag}:{option}")
+    out["pred_cases"] = np.array(ptags)
+
+    # the PD check on tensors (array_operations.py:75-103)
+    a = rng.standard_normal((4, 5, 7))
+    pd = a @ np.swapaxes(a, 1, 2) + 0.1 * np.eye(5)
+    not_pd = pd.copy(); not_pd[2] -= 3.0 * np.linalg.eigvalsh(pd[2]).max() * np.eye(5)
+    asym = pd.copy(); asym[1, 0, 3] += 1e-3
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["pd_inputs"] = np.stack([pd, not_pd, asym])
+        out["pd_truth"] = np.array([are_all_positive_definite(tf.constant(m)) for m in (pd, not_pd, asym)])
+
+    # JSON checkpoints written by the reference's save_model_params_dict, and what its load_from_params_dict
+    # assigns from them (wishart_process.py:239-308, 526-602)
+    class _Obj:
+        pass
+
+    def fake(cls, D, M, option, sparse):
+        m = object.__new__(cls)
+        m.D, m.nu = D, D
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.likelihood = WishartProcessLikelihood(D=D, A_scale_matrix_option=option, train_additive_noise=True,
+                                                    verbose=False)
+        m.kernel = _Obj()
+        m.kernel.variance = tf.Variable(1.0)
+        m.kernel.lengthscales = tf.Variable(0.3)
+        if sparse:
+            m.inducing_variable = _Obj()
+            m.inducing_variable.Z = tf.Variable(np.linspace(0, 1, M)[:, None])
+        m.q_mu = tf.Variable(np.zeros((M, D * D)))
+        m.q_sqrt = tf.Variable(np.tile(1e-3 * np.eye(M)[None], (D * D, 1, 1)))
+        return m
+
+    def randomise(m, sparse):
+        lik = m.likelihood
+        lik.A_scale_matrix.assign(lik.A_scale_matrix.numpy() + 0.1 * rng.standard_normal(lik.A_scale_matrix.shape))
+        lik.additive_part.assign(lik.additive_part.numpy() + 0.3 * rng.standard_normal(lik.additive_part.shape))
+        m.kernel.variance.assign(1.0 + rng.random())
+        m.kernel.lengthscales.assign(0.2 + rng.random())
+        if sparse:
+            m.inducing_variable.Z.assign(np.sort(rng.random(m.inducing_variable.Z.shape), axis=0))
+        m.q_mu.assign(rng.standard_normal(m.q_mu.shape))
+        m.q_sqrt.assign(np.tril(rng.standard_normal(m.q_sqrt.shape)))
+
+    logging_off = __import__("logging").disable
+    logging_off(50)
+    for fname, cls, D, M, option, sparse in [("svwp_reference_params.json", SparseVariationalWishartProcess, 2, 3, "train_full_matrix", True),
+                                             ("svwp_diag_reference_params.json", SparseVariationalWishartProcess, 3, 2, "train_diagonal", True),
+                                             ("vwp_reference_params.json", VariationalWishartProcess, 2, 4, "train_full_matrix", False)]:
+        m = fake(cls, D, M, option, sparse)
+        randomise(m, sparse)
+        with tempfile.TemporaryDirectory() as d:
+            m.save_model_params_dict(d, fname)
+            text = open(os.path.join(d, fname)).read()
+            # a fresh model of the class the reference can load this file into (a 1-D A becomes diag(A) for SVWP)
+            m2 = fake(cls, D, M, "train_full_matrix" if sparse else option, sparse)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m2.load_from_params_dict(d, fname)
+        open(os.path.join(HERE, fname), "w").write(text)
+        key = fname.replace("_reference_params.json", "")
+        out[f"json_{key}_A"] = m2.likelihood.A_scale_matrix.numpy().copy()
+        out[f"json_{key}_lam"] = m2.likelihood.additive_part.numpy().copy()
+        out[f"json_{key}_kvar"] = np.array(float(m2.kernel.variance.numpy()))
+        out[f"json_{key}_kls"] = np.array(float(m2.kernel.lengthscales.numpy()))
+        out[f"json_{key}_q_mu"] = m2.q_mu.numpy().copy()
+        out[f"json_{key}_q_sqrt"] = m2.q_sqrt.numpy().copy()
+        if sparse:
+            out[f"json_{key}_Z"] = m2.inducing_variable.Z.numpy().copy()
+        assert list(json.loads(text).keys()) == (["D", "nu", "A_scale_matrix", "additive_noise", "kernel_variance",
+                                                  "kernel_lengthscales"] + (["Z"] if sparse else []) + ["q_mu", "q_sqrt"])
+    logging_off(0)
+    np.savez_compressed(os.path.join(HERE, "wishart_reference.npz"), **out)
+    print("reference-source wishart fixtures written:", os.path.getsize(os.path.join(HERE, "wishart_reference.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wishart", "sliding", "filtering", "summary", "csv"]
+    which = sys.argv[1:] or ["wishart", "sliding", "filtering", "summary", "csv", "wishart_reference"]
+    if "wishart_reference" in which:
+        import subprocess
+        if len(which) > 1:   # own process: the tensorflow stand-in must not leak into the other generators
+            subprocess.run([sys.executable, os.path.abspath(__file__), "wishart_reference"], check=True)
+            which = [w for w in which if w != "wishart_reference"]
+        else:
+            make_wishart_reference()
+            sys.exit(0)
     if "summary" in which:
         make_summary()
     if "csv" in which:
@@ -188,5 +398,7 @@ if __name__ == "__main__":
         make_wishart()
     if "sliding" in which:
         make_sliding()
+    if "sliding_c3" in which:   # not in the default list: takes minutes
+        make_sliding_c3()
     if "filtering" in which:
         make_filtering()

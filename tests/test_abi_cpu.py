@@ -57,3 +57,19 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"
+
+
+def test_synthetic_inputs_equal_the_checker_inputs():
+    """bench.py's CUDA arm builds its inputs with fcest_b200.helpers.synthetic (no oracle import on the product
+    side); the CPU arm uses oracle.wishart_oracle.make_inputs.  Same seed -> identical arrays."""
+    import numpy as np
+    from fcest_b200.helpers.synthetic import make_synthetic
+    from oracle import wishart_oracle as wo
+    for kw in (dict(N=30, D=4, S=3, M=9, seed=2), dict(N=12, D=3, S=2, M=None, seed=5, a_option="scaled"),
+               dict(N=10, D=3, S=2, M=4, seed=1, perturbed=False, a_option="train_diagonal")):
+        s = make_synthetic(**kw)
+        x, y, eps, p = wo.make_inputs(**kw)
+        assert np.array_equal(s["x"], x.numpy()) and np.array_equal(s["y"], y.numpy())
+        assert np.array_equal(s["eps"], eps.numpy())
+        for k in ("Z", "q_mu", "q_sqrt", "A", "lam"):
+            assert np.array_equal(s[k], p[k].numpy()), k

@@ -304,3 +304,54 @@ def test_csv_layout_matches_reference_round_trip():
     assert np.abs(np.asarray(got, dtype=np.float64)[1:] - cov).max() <= 1e-15    # what was saved is the estimate
     assert np.array_equal(to_3d_format(to_2d_format(cov)), np.swapaxes(cov, 1, 2))
     assert to_2d_format(cov).shape == (9, 12)
+
+
+# ---- Wishart path: oracle vs outputs of the reference's OWN source (likelihoods.py / wishart_process.py /
+#      array_operations.py executed on the NumPy tensorflow stand-in, tests/golden/make_golden.py) -------------
+def _ref_cases(g, key):
+    return [c.split(":") for c in g[key].tolist()]
+
+
+def test_wishart_oracle_matches_reference_source_likelihood():
+    g = np.load(os.path.join(GOLD, "wishart_reference.npz"))
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+    for tag, option in _ref_cases(g, "lik_cases"):
+        A, lam, y = t(g[f"lik_{tag}_A"]), t(g[f"lik_{tag}_lam"]), t(g[f"lik_{tag}_y"])
+        ve = wo.variational_expectations(t(g[f"lik_{tag}_f_mean"]), t(g[f"lik_{tag}_f_var"]), y, A, lam,
+                                         t(g[f"lik_{tag}_eps"]))
+        ref = g[f"lik_{tag}_ve"]
+        assert np.abs(ve.numpy() - ref).max() <= 1e-11 * np.abs(ref).max(), tag
+        lp = wo.log_prob(t(g[f"lik_{tag}_f_sample"]), y, A, lam)
+        ref = g[f"lik_{tag}_log_prob"]
+        assert np.abs(lp.numpy() - ref).max() <= 1e-11 * np.abs(ref).max(), tag
+        noise = wo.add_diagonal_additive_noise(t(g[f"lik_{tag}_cov_in"]), lam)
+        assert np.abs(noise.numpy() - g[f"lik_{tag}_cov_noise"]).max() <= 1e-14
+        # constructor state (likelihoods.py:64-86, 208-251) against the oracle's canonical initial point
+        D = y.shape[1]
+        _, _, _, p = wo.make_inputs(4, D, 1, M=3, perturbed=False, a_option=option)
+        assert np.array_equal(p["A"].numpy(), g[f"lik_{tag}_A_init"])
+        assert np.abs(p["lam"].numpy() - g[f"lik_{tag}_lam_init"]).max() <= 1e-15
+        dims = g[f"lik_{tag}_dims"]
+        assert tuple(dims[:5]) == (1, D * D, D, D, D)
+        assert bool(dims[5]) == (option in ("train_full_matrix", "train_diagonal")) and bool(dims[6])
+    assert str(g["nu_lt_D_message"]) == "Wishart Degrees of Freedom must be >= D."
+
+
+def test_wishart_oracle_matches_reference_source_prediction():
+    g = np.load(os.path.join(GOLD, "wishart_reference.npz"))
+    t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+    for tag, option in _ref_cases(g, "pred_cases"):
+        A, lam = t(g[f"pred_{tag}_A"]), t(g[f"pred_{tag}_lam"])
+        fm, fv, eps = t(g[f"pred_{tag}_f_mean"]), t(g[f"pred_{tag}_f_var"]), t(g[f"pred_{tag}_eps"])
+        D = lam.shape[0]
+        s = wo.cov_samples(fm, fv, A, lam, eps, D)
+        assert np.abs(s.numpy() - g[f"pred_{tag}_samples"]).max() <= 1e-12 * np.abs(g[f"pred_{tag}_samples"]).max()
+        c = wo.convert_tensor_to_correlation(s)
+        assert np.abs(c.numpy() - g[f"pred_{tag}_corr_samples"]).max() <= 1e-13
+        for fn, key in ((wo.predict_cov, "cov"), (wo.predict_corr, "corr")):
+            mean, std = fn(fm, fv, A, lam, eps, D)
+            scale = np.abs(g[f"pred_{tag}_{key}_mean"]).max()
+            assert np.abs(mean.numpy() - g[f"pred_{tag}_{key}_mean"]).max() <= 1e-12 * scale, (tag, key)
+            assert np.abs(std.numpy() - g[f"pred_{tag}_{key}_std"]).max() <= 1e-12 * scale, (tag, key)
+    truth = [wo.are_all_positive_definite(m) for m in g["pd_inputs"]]
+    assert truth == g["pd_truth"].tolist() == [True, False, False]

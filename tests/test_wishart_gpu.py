@@ -465,3 +465,46 @@ def test_full_size_properties_c4(cuda):
         fd = (ep - em) / (2 * h)
         an = float((gq.reshape(-1) * d.reshape(-1)).sum().item())
         assert abs(fd - an) <= 1e-4 * abs(an), (q.name, fd, an)
+
+
+def test_elbo_raises_on_failed_cholesky(cuda):
+    """model.elbo() inspects the Cholesky status like elbo_and_grad (tf.linalg.cholesky raises in the reference,
+    likelihoods.py:184-189): Sigma = 0 when A = 0 and softplus(lambda) underflows."""
+    m, x, y, eps, p = _build("svgp", 20, 3, 2, 6)
+    m.likelihood.A_scale_matrix.assign(np.zeros((3, 3)))
+    m.likelihood.additive_part.assign(np.full(3, -800.0))
+    with pytest.raises(RuntimeError):
+        m.elbo((x.numpy(), y.numpy()), epsilon=eps.cuda())
+    with pytest.raises(RuntimeError):
+        m.elbo_and_grad((x.numpy(), y.numpy()), epsilon=eps.cuda())
+    assert not np.isfinite(m.elbo((x.numpy(), y.numpy()), epsilon=eps.cuda(), check=False).item())
+
+
+def test_graph_replay_survives_a_larger_eager_workspace_request(cuda):
+    """A captured training step holds raw pointers into the split-K scratch buffers; an eager GEMM that outgrows
+    the cached buffer between replays must not free them (ops._workspace retires, never releases)."""
+    from fcest_b200 import ops
+    from fcest_b200.helpers.inference import GraphedTrainingStep, KerasAdam
+    m, x, y, eps, p = _build("svgp", 40, 4, 3, 12)
+    m2, *_ = _build("svgp", 40, 4, 3, 12)
+    data = (x.numpy(), y.numpy())
+    for mm in (m, m2):
+        mm.likelihood.seed(9)
+    g = GraphedTrainingStep(m, data, KerasAdam(m.trainable_parameters))
+    ref = GraphedTrainingStep(m2, data, KerasAdam(m2.trainable_parameters))
+    for _ in range(3):
+        g(); ref()
+    before = dict(ops._ws_cache)
+    # outgrow every cached scratch buffer on this device's streams, then release what the allocator can reuse
+    for key, buf in before.items():
+        s = torch.cuda.ExternalStream(key[1]) if key[1] else torch.cuda.default_stream()
+        with torch.cuda.stream(s):
+            ops._workspace(buf.numel() * 8 + (4 << 20), buf.device)
+    assert all(any(b is r for r in ops._ws_retired) for b in before.values())
+    junk = [torch.full((1 << 18,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(16)]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        g(); ref()
+    del junk
+    assert _rel(m.q_sqrt.unconstrained.cpu().numpy(), m2.q_sqrt.unconstrained.cpu().numpy()) < 1e-13
+    assert _rel(m.q_mu.unconstrained.cpu().numpy(), m2.q_mu.unconstrained.cpu().numpy()) < 1e-13
