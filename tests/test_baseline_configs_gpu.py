@@ -34,7 +34,9 @@ def _assign(m, p):
     m.likelihood.additive_part.assign(p["lam"])
 
 
-def _check_grads(m, g_ref, sparse, tol=1e-7):
+def _check_grads(m, g_ref, sparse, tol=1e-7, floor=0.0):
+    """Each gradient to ``tol`` relative to its largest reference entry (``floor``: lower bound of that scale, for a
+    gradient that is analytically zero at the evaluation point)."""
     got = {"q_mu": m.q_mu.grad, "q_sqrt": m.q_sqrt.grad, "A": m.likelihood.A_scale_matrix.grad,
            "lam": m.likelihood.additive_part.grad, "u_var": m.kernel.variance.grad,
            "u_ls": m.kernel.lengthscales.grad}
@@ -42,7 +44,8 @@ def _check_grads(m, g_ref, sparse, tol=1e-7):
         got["Z"] = m.inducing_variable.Z.grad
     worst = {}
     for k, v in got.items():
-        worst[k] = _rel(v.cpu().numpy(), g_ref[k].numpy())
+        ref = g_ref[k].numpy().reshape(-1)
+        worst[k] = float(np.abs(v.cpu().numpy().reshape(-1) - ref).max() / max(np.abs(ref).max(), floor, 1e-300))
         assert worst[k] < tol, (k, worst[k])
     return worst
 
@@ -80,7 +83,9 @@ def test_c1_vwp_at_reference_initialisation(cuda):
     elbo_ref, g_ref = wo.elbo_and_grad("vgp", p, x, y, eps)
     elbo = m.elbo_and_grad(None, epsilon=eps.cuda()).item()
     assert abs(elbo - elbo_ref) <= 1e-8 * abs(elbo_ref), (elbo, elbo_ref)
-    _check_grads(m, g_ref, sparse=False)
+    # with q_mu = 0 and q_sqrt = c I the VGP moments do not depend on the lengthscale: d ELBO / d u_ls is zero
+    # analytically (oracle: -6e-17, rounding), so it is held to the scale of the kernel-variance gradient
+    _check_grads(m, g_ref, sparse=False, floor=float(g_ref["u_var"].abs().max()))
 
 
 def test_c2_svwp(cuda):
