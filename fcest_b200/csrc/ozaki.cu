@@ -1,0 +1,612 @@
+// fp64 GEMM on the 5th-generation tensor cores: Ozaki-style int8-slice emulation (tcgen05.mma kind::i8, int32
+// accumulators in TMEM, operand tiles staged by TMA).
+//
+// Why: the three projection GEMMs  V = Pk Sk^T,  Gk = g^T Pk,  Tk = g Sk   are 98 % of
+// the flops of an ELBO + gradient evaluation and the native fp64 tensor path (DMMA, 37 TFLOP/s) has no tcgen05 form.
+// The int8 tensor pipe is ~100x wider, so an error-bounded split of the fp64 operands into 7-bit digits wins even
+// though ns (ns + 1) / 2 integer GEMMs replace one fp64 GEMM.
+//
+// Arithmetic.  Every operand row (a vector along the contraction axis) is scaled by a power of two into (-1, 1) and
+// cut into ns balanced base-128 digits q_s in [-64, 64]:   x = 2^e sum_s q_s 2^(-6 - 7 s)   (exact operations: power-
+// of-two scaling, rint, subtraction).  The product keeps the digit pairs with s + t < ns:
+//     C[i][j] = 2^(eA_i + eB_j - 12) sum_{d < ns} 2^(-7 d) sum_{s + t = d} (A_s B_t^T)[i][j]
+// Each inner sum is an EXACT integer GEMM (|q| <= 64, int32 accumulation, at most 8 pairs x 65536 terms per
+// accumulator); the sum over d runs in fp64, least significant order first (Horner).  Dropped terms are bounded by
+// (ns + 1) K 2^(-7 ns) relative to max|A_i| max|B_j| -- measured at C4: 6e-13 of the largest entry for ns = 7
+// (profiles/r02_ozaki_accuracy_cpu_study.txt).
+//
+// Kernel (persistent, one CTA per SM, 10 warps):
+//   warp 0 (one lane)  TMA producer: per 64-byte K block the B tile set (all digits needed by the pass, two stages)
+//                      and the A tiles (ring of 12), cp.async.bulk.tensor.4d with mbarrier complete_tx
+//   warp 1 (one lane)  MMA issuer: for every (s, t) of the pass two tcgen05.mma (K = 32 each) into the TMEM
+//                      accumulator of order d = s + t; tcgen05.commit releases operand slots / publishes accumulators
+//   warps 2-9          epilogue: tcgen05.ld of a finished order, int32 -> fp64, Horner step; after the last order
+//                      scale by the row / column exponents and store (or write a split-K partial)
+// All digits of a K block are resident together, so one tile of A_s meets every B_t it pairs with: 10 tile loads per
+// 28 tile products at ns = 7 (a pair-by-pair loop would need 56).  TMEM holds four 128 x 128 int32 accumulators:
+// orders are processed in passes of four (d = ns-1 .. ns-4, then the rest).
+// Work units = (K split, 128 x 128 output tile), dealt round-robin to the CTAs in K-split-major order so that
+// concurrently running CTAs stream the same K range (the digit arrays of one K split stay L2 resident).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "fcest_b200.h"
+
+namespace fcest {
+namespace oz {
+
+constexpr int TM = 128, TN = 128;       // output tile
+constexpr int KB = 64;                   // bytes (= int8 elements) of K per staged block
+constexpr int TILE_BYTES = TM * KB;      // 8 KB per digit tile
+constexpr int MAX_NS = 8;
+constexpr int B_STAGES = 2;
+constexpr int A_SLOTS = 12;
+constexpr int NUM_THREADS = 320;         // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int SMEM_B = B_STAGES * MAX_NS * TILE_BYTES;
+constexpr int SMEM_A = A_SLOTS * TILE_BYTES;
+constexpr int SMEM_BAR = 512;
+constexpr int SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_BAR + 1024;  // + alignment slack
+
+struct Params {
+  int M, N, tiles_m, tiles_n, nkb, ksplit, ns;
+  double alpha;
+  const double* rsA;       // (tiles_m * 128) row scales 2^(e - 6) of op(A) rows
+  const double* rsB;       // (tiles_n * 128) scales of op(B) rows (= output columns)
+  const double* bias_row;  // (M) or null
+  double* C;
+  long long ldc;
+  double* partial;         // ksplit > 1: [ksplit][tiles][128 * 128] unscaled Horner sums
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], int8 x int8 -> int32, M = 128, N = 128, K = 32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile of 128 rows x 64 bytes written by TMA with the 64-byte swizzle: rows 64 B apart, 8-row
+// groups 512 B apart (SBO), descriptor version 1 (Blackwell), layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                        // descriptor version
+  d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
+  return d;
+}
+// kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+struct PassInfo {
+  int d_hi, d_lo, nsl;
+};
+__device__ __forceinline__ PassInfo pass_info(int ns, int p) {
+  PassInfo q;
+  q.d_hi = ns - 1 - 4 * p;
+  q.d_lo = q.d_hi - 3 > 0 ? q.d_hi - 3 : 0;
+  q.nsl = q.d_hi + 1;
+  return q;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smB = base;                  // [stage][digit][8 KB]
+  const uint32_t smA = base + SMEM_B;         // [slot][8 KB]
+  const uint32_t bars = smA + SMEM_A;
+  const uint32_t fullB = bars, emptyB = bars + 16, fullA = bars + 32, emptyA = fullA + 8 * A_SLOTS;
+  const uint32_t tfull = emptyA + 8 * A_SLOTS, tempty = tfull + 32, tptr = tempty + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ns = p.ns, npass = (ns + 3) >> 2;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int units = tiles * p.ksplit;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
+    for (int i = 0; i < A_SLOTS; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int a_slot = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int ks = u / tiles, tile = u - ks * tiles;
+        const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;
+        const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
+        for (int ps = 0; ps < npass; ++ps) {
+          const PassInfo pi = pass_info(ns, ps);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(emptyB + 8 * b_stage, b_phase ^ 1u);
+            mbar_expect_tx(fullB + 8 * b_stage, (uint32_t)(pi.nsl * TILE_BYTES));
+            for (int t = 0; t < pi.nsl; ++t)
+              tma_load_4d(smB + (b_stage * MAX_NS + t) * TILE_BYTES, &tmB, fullB + 8 * b_stage, 0, tn * TN, kb, t);
+            if (++b_stage == B_STAGES) { b_stage = 0; b_phase ^= 1u; }
+            for (int s = 0; s < pi.nsl; ++s) {
+              mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1u);
+              mbar_expect_tx(fullA + 8 * a_slot, (uint32_t)TILE_BYTES);
+              tma_load_4d(smA + a_slot * TILE_BYTES, &tmA, fullA + 8 * a_slot, 0, tm * TM, kb, s);
+              if (++a_slot == A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      int a_slot = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      uint32_t use[4] = {0, 0, 0, 0};  // how often each accumulator has been handed to the epilogue
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int ks = u / tiles;
+        const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
+        for (int ps = 0; ps < npass; ++ps) {
+          const PassInfo pi = pass_info(ns, ps);
+          const int nbuf = pi.d_hi - pi.d_lo + 1;
+          for (int b = 0; b < nbuf; ++b) mbar_wait(tempty + 8 * b, (use[b] & 1u) ^ 1u);  // drained by the epilogue
+          tc_fence_after();
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(fullB + 8 * b_stage, b_phase);
+            const uint32_t bset = smB + b_stage * MAX_NS * TILE_BYTES;
+            for (int s = 0; s < pi.nsl; ++s) {
+              mbar_wait(fullA + 8 * a_slot, a_phase);
+              tc_fence_after();
+              const uint64_t da = make_smem_desc(smA + a_slot * TILE_BYTES);
+              const int t_lo = pi.d_lo - s > 0 ? pi.d_lo - s : 0, t_hi = pi.d_hi - s;
+              for (int t = t_lo; t <= t_hi; ++t) {
+                const uint64_t db = make_smem_desc(bset + t * TILE_BYTES);
+                const uint32_t acc = tmem_base + (uint32_t)((pi.d_hi - (s + t)) * TN);
+                const uint32_t keep = (kb > kb0 || s > 0) ? 1u : 0u;  // first product of this order in the unit
+                umma_i8(acc, da, db, kInstrDesc, keep);
+                umma_i8(acc, da + 2, db + 2, kInstrDesc, 1u);         // second K = 32 step: +32 bytes
+              }
+              tc_commit(emptyA + 8 * a_slot);
+              if (++a_slot == A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+            }
+            tc_commit(emptyB + 8 * b_stage);
+            if (++b_stage == B_STAGES) { b_stage = 0; b_phase ^= 1u; }
+          }
+          for (int b = 0; b < nbuf; ++b) { tc_commit(tfull + 8 * b); ++use[b]; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue warps =====================================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;    // column half of the tile
+    const int rloc = q * 32 + lane;
+    uint32_t use[4] = {0, 0, 0, 0};
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int ks = u / tiles, tile = u - ks * tiles;
+      const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;
+      double S[64];
+      bool first = true;
+      for (int ps = 0; ps < npass; ++ps) {
+        const PassInfo pi = pass_info(ns, ps);
+        for (int d = pi.d_hi; d >= pi.d_lo; --d) {
+          const int b = pi.d_hi - d;
+          mbar_wait(tfull + 8 * b, use[b] & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TN + half * 64 + c * 32), v);
+            tmem_ld_wait();
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) S[c * 32 + j] = (double)(int)v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) S[c * 32 + j] = fma(S[c * 32 + j], 0.0078125, (double)(int)v[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + 8 * b);
+          ++use[b];
+          first = false;
+        }
+      }
+      const int row = tm * TM + rloc;
+      const int col0 = tn * TN + half * 64;
+      if (p.ksplit == 1) {
+        if (row < p.M) {
+          const double sr = p.rsA[row] * p.alpha;
+          const double br = p.bias_row ? p.bias_row[row] : 0.0;
+          double* crow = p.C + (long long)row * p.ldc;
+          if (col0 + 64 <= p.N && ((p.ldc & 1) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              const double2 sc = *reinterpret_cast<const double2*>(p.rsB + col0 + j);
+              double2 o;
+              o.x = S[j] * sr * sc.x + br;
+              o.y = S[j + 1] * sr * sc.y + br;
+              *reinterpret_cast<double2*>(crow + col0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = S[j] * sr * p.rsB[col0 + j] + br;
+          }
+        }
+      } else {
+        double* dst = p.partial + ((long long)ks * tiles + tile) * (TM * TN) + rloc * TN + half * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(S[j], S[j + 1]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Sum of the K-split partials in fixed order, exponent scaling, bias.  grid (tiles, 16), 256 threads: 8 rows x 128 cols.
+__global__ void __launch_bounds__(256) ozaki_fixup_kernel(const Params p) {
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int tile = blockIdx.x;
+  const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;
+  const int rloc = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int cloc = (threadIdx.x & 31) * 4;
+  const int row = tm * TM + rloc;
+  if (row >= p.M) return;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int ks = 0; ks < p.ksplit; ++ks) {
+    const double* src = p.partial + ((long long)ks * tiles + tile) * (TM * TN) + rloc * TN + cloc;
+    const double2 a = *reinterpret_cast<const double2*>(src), b = *reinterpret_cast<const double2*>(src + 2);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+  }
+  const double sr = p.rsA[row] * p.alpha;
+  const double br = p.bias_row ? p.bias_row[row] : 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = tn * TN + cloc + j;
+    if (col < p.N) p.C[(long long)row * p.ldc + col] = acc[j] * sr * p.rsB[col] + br;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// digit extraction
+// ---------------------------------------------------------------------------------------------------------------
+// biased exponent field E of max|x| -> (input scale 2^(6 - e), output scale 2^(e - 6)), e = E - 1022; zero / tiny rows -> 0
+__device__ __forceinline__ void scales_from_exp(uint32_t E, double& s_in, double& s_out) {
+  if (E < 8u || E > 2040u) { s_in = 0.0; s_out = 0.0; return; }
+  s_in = __longlong_as_double((long long)(2051u - E) << 52);
+  s_out = __longlong_as_double((long long)(E - 5u) << 52);
+}
+
+// Operand stored with the contraction axis contiguous: X (rows, Kc), row pitch ld.  One CTA per (padded) output row.
+// out[((s * nkb + kb) * rows_pad + row) * 64 + k % 64]
+__global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ X, long long ld, int rows, int Kc,
+                                                         int rows_pad, int nkb, int ns, int8_t* __restrict__ out,
+                                                         double* __restrict__ rs) {
+  __shared__ uint32_t redE[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const bool live = row < rows;
+  const double* x = X + (long long)row * ld;
+  uint32_t E = 0;
+  if (live) {
+    for (int k = tid; k < Kc; k += 256) {
+      const uint32_t e = ((uint32_t)(__double_as_longlong(x[k]) >> 52)) & 0x7FFu;
+      E = e > E ? e : E;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const uint32_t t = __shfl_xor_sync(0xffffffffu, E, o); E = t > E ? t : E; }
+  if ((tid & 31) == 0) redE[tid >> 5] = E;
+  __syncthreads();
+  E = redE[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) E = redE[w] > E ? redE[w] : E;
+  double s_in, s_out;
+  scales_from_exp(E, s_in, s_out);
+  if (tid == 0) rs[row] = live ? s_out : 0.0;
+  const int Kp = nkb * KB;
+  for (int k8 = tid * 8; k8 < Kp; k8 += 256 * 8) {
+    double t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = (live && k8 + i < Kc) ? x[k8 + i] * s_in : 0.0;
+    const int kb = k8 >> 6;
+    int8_t* dst = out + ((long long)kb * rows_pad + row) * KB + (k8 & 63);
+    for (int s = 0; s < ns; ++s) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double qd = rint(t[i]);
+        t[i] = (t[i] - qd) * 128.0;
+        const uint32_t b = (uint32_t)((int)qd) & 0xFFu;
+        if (i < 4) lo |= b << (8 * i); else hi |= b << (8 * (i - 4));
+      }
+      *reinterpret_cast<uint2*>(dst + (long long)s * nkb * rows_pad * KB) = make_uint2(lo, hi);
+    }
+  }
+}
+
+// Operand stored with the contraction axis strided: X (Kc, cols), pitch ld; output rows = columns of X.
+__global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ X, long long ld, int Kc, int cols,
+                                                     uint32_t* __restrict__ Eout) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= cols) return;
+  const int k0 = blockIdx.y * 64, k1 = min(Kc, k0 + 64);
+  uint32_t E = 0;
+  for (int k = k0; k < k1; ++k) {
+    const uint32_t e = ((uint32_t)(__double_as_longlong(X[(long long)k * ld + j]) >> 52)) & 0x7FFu;
+    E = e > E ? e : E;
+  }
+  atomicMax(Eout + j, E);   // order independent: deterministic
+}
+
+// grid (cols_pad / 64, nkb), 256 threads: 64 contraction steps x 64 columns -> ns x 64 rows of 64 bytes
+__global__ void __launch_bounds__(256) split_cols_kernel(const double* __restrict__ X, long long ld, int Kc, int cols,
+                                                         int cols_pad, int nkb, int ns,
+                                                         const uint32_t* __restrict__ Ein, int8_t* __restrict__ out,
+                                                         double* __restrict__ rs) {
+  __shared__ uint32_t tile[MAX_NS][64][17];  // [digit][column][k / 4], 17-word pitch: conflict-free column writes
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+  const int j = blockIdx.x * 64 + tx, kb = blockIdx.y;
+  double s_in = 0.0, s_out = 0.0;
+  if (j < cols) scales_from_exp(Ein[j], s_in, s_out);
+  if (kb == 0 && ty == 0) rs[j] = s_out;
+  for (int g = ty; g < 16; g += 4) {   // group of 4 consecutive contraction steps
+    double t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kb * 64 + 4 * g + i;
+      t[i] = (j < cols && k < Kc) ? X[(long long)k * ld + j] * s_in : 0.0;
+    }
+    for (int s = 0; s < ns; ++s) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double qd = rint(t[i]);
+        t[i] = (t[i] - qd) * 128.0;
+        w |= ((uint32_t)((int)qd) & 0xFFu) << (8 * i);
+      }
+      tile[s][tx][g] = w;
+    }
+  }
+  __syncthreads();
+  // write: per digit and column one 64-byte row = 4 x 16 bytes
+  for (int c = tid; c < ns * 64 * 4; c += 256) {
+    const int s = c / 256, rem = c - s * 256, col = rem >> 2, part = rem & 3;
+    const uint32_t* src = &tile[s][col][part * 4];
+    const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+    int8_t* dst = out + (((long long)s * nkb + kb) * cols_pad + blockIdx.x * 64 + col) * KB + part * 16;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// digits[s][kb][row][64 bytes]  ->  rank-4 map, box = one 128-row x 64-byte tile, 64-byte swizzle
+static int make_map(CUtensorMap* map, void* base, int rows_pad, int nkb, int ns) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return FCEST_ERR_UNSUPPORTED;
+  const cuuint64_t dims[4] = {(cuuint64_t)KB, (cuuint64_t)rows_pad, (cuuint64_t)nkb, (cuuint64_t)ns};
+  const cuuint64_t strides[3] = {(cuuint64_t)KB, (cuuint64_t)rows_pad * KB, (cuuint64_t)nkb * rows_pad * KB};
+  const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)TM, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : FCEST_ERR_ARGUMENT;
+}
+
+static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+struct Plan {
+  int Mp, Np, tiles_m, tiles_n, nkb, ksplit;
+  long long offA, offB, off_rsA, off_rsB, off_E, off_part, total;
+};
+
+static Plan make_plan(int M, int N, int K, int ns, int sms) {
+  Plan pl;
+  pl.Mp = (int)round_up(M, TM);
+  pl.Np = (int)round_up(N, TN);
+  pl.tiles_m = pl.Mp / TM;
+  pl.tiles_n = pl.Np / TN;
+  pl.nkb = (int)((K + KB - 1) / KB);
+  const int tiles = pl.tiles_m * pl.tiles_n;
+  // K split: fewest splits within 3 % of the best wave efficiency; every unit keeps >= 8 K blocks and at most 1024
+  // (int32 accumulators: 8 pairs x 65536 terms x 64^2 < 2^31)
+  int ks_min = (pl.nkb + 1023) / 1024, best = ks_min;
+  double best_cost = 1e300;
+  for (int ks = ks_min; ks <= 16; ++ks) {
+    if (ks > ks_min && pl.nkb / ks < 8) break;
+    const double cost = (double)((tiles * (long long)ks + sms - 1) / sms) / ks;
+    if (cost < best_cost * 0.97) { best_cost = cost; best = ks; }
+  }
+  pl.ksplit = best < 1 ? 1 : best;
+  long long o = 0;
+  pl.offA = o; o += round_up((long long)ns * pl.nkb * pl.Mp * KB, 1024);
+  pl.offB = o; o += round_up((long long)ns * pl.nkb * pl.Np * KB, 1024);
+  pl.off_rsA = o; o += round_up((long long)pl.Mp * 8, 1024);
+  pl.off_rsB = o; o += round_up((long long)pl.Np * 8, 1024);
+  pl.off_E = o; o += round_up((long long)(pl.Mp > pl.Np ? pl.Mp : pl.Np) * 4, 1024);
+  pl.off_part = o;
+  if (pl.ksplit > 1) o += (long long)pl.ksplit * tiles * TM * TN * 8;
+  pl.total = o + 1024;  // slack for aligning the caller's pointer
+  return pl;
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// digits of op(X): `kmajor` = contraction axis contiguous (rows, Kc), else X is (Kc, rows)
+static int split_operand(const double* X, long long ld, int kmajor, int rows, int Kc, int rows_pad, int nkb, int ns,
+                         int8_t* out, double* rs, uint32_t* Etmp, cudaStream_t stream) {
+  if (kmajor) {
+    split_rows_kernel<<<rows_pad, 256, 0, stream>>>(X, ld, rows, Kc, rows_pad, nkb, ns, out, rs);
+    FCEST_CHECK_LAUNCH();
+  } else {
+    cudaError_t e = cudaMemsetAsync(Etmp, 0, (size_t)rows_pad * 4, stream);
+    if (e != cudaSuccess) return (int)e;
+    colmax_kernel<<<dim3((rows + 255) / 256, (Kc + 63) / 64), 256, 0, stream>>>(X, ld, Kc, rows, Etmp);
+    FCEST_CHECK_LAUNCH();
+    split_cols_kernel<<<dim3(rows_pad / 64, nkb), 256, 0, stream>>>(X, ld, Kc, rows, rows_pad, nkb, ns, Etmp, out, rs);
+    FCEST_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace oz
+}  // namespace fcest
+
+using namespace fcest;
+
+extern "C" long long fcest_dgemm_ozaki_workspace_bytes(int M, int N, int K, int slices) {
+  if (M < 1 || N < 1 || K < 1 || slices < 2 || slices > oz::MAX_NS) return 0;
+  return oz::make_plan(M, N, K, slices, oz::sm_count()).total;
+}
+
+extern "C" int fcest_dgemm_ozaki(int a_kmajor, int b_kmajor, int M, int N, int K, double alpha, const double* A,
+                                 long long lda, const double* B, long long ldb, double* C, long long ldc,
+                                 const double* bias_row, int slices, void* workspace, long long workspace_bytes,
+                                 cudaStream_t stream) {
+  if (M < 1 || N < 1 || K < 1 || slices < 2 || slices > oz::MAX_NS || !A || !B || !C || !workspace)
+    return FCEST_ERR_ARGUMENT;
+  const int sms = oz::sm_count();
+  const oz::Plan pl = oz::make_plan(M, N, K, slices, sms);
+  if (workspace_bytes < pl.total) return FCEST_ERR_ARGUMENT;
+  uint8_t* ws = (uint8_t*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  int8_t* dA = (int8_t*)(ws + pl.offA);
+  int8_t* dB = (int8_t*)(ws + pl.offB);
+  double* rsA = (double*)(ws + pl.off_rsA);
+  double* rsB = (double*)(ws + pl.off_rsB);
+  uint32_t* Etmp = (uint32_t*)(ws + pl.off_E);
+  int rc = oz::split_operand(A, lda, a_kmajor, M, K, pl.Mp, pl.nkb, slices, dA, rsA, Etmp, stream);
+  if (rc) return rc;
+  rc = oz::split_operand(B, ldb, b_kmajor, N, K, pl.Np, pl.nkb, slices, dB, rsB, Etmp, stream);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  rc = oz::make_map(&tmA, dA, pl.Mp, pl.nkb, slices);
+  if (rc) return rc;
+  rc = oz::make_map(&tmB, dB, pl.Np, pl.nkb, slices);
+  if (rc) return rc;
+  oz::Params p;
+  p.M = M; p.N = N; p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.nkb = pl.nkb; p.ksplit = pl.ksplit; p.ns = slices;
+  p.alpha = alpha; p.rsA = rsA; p.rsB = rsB; p.bias_row = bias_row; p.C = C; p.ldc = ldc;
+  p.partial = (double*)(ws + pl.off_part);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int units = pl.tiles_m * pl.tiles_n * pl.ksplit;
+  const int grid = units < sms ? units : sms;
+  oz::ozaki_gemm_kernel<<<grid, oz::NUM_THREADS, oz::SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  FCEST_CHECK_LAUNCH();
+  if (pl.ksplit > 1) {
+    oz::ozaki_fixup_kernel<<<dim3(pl.tiles_m * pl.tiles_n, 16), 256, 0, stream>>>(p);
+    FCEST_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -5,6 +5,8 @@ current CUDA stream to ``libfcest_b200.so``.  No arithmetic happens in Python.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -53,9 +55,33 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+# Large GEMMs go to the int8 tensor cores (tcgen05 Ozaki-style emulation, ``fcest_dgemm_ozaki``) unless
+# FCEST_GEMM_IMPL=dmma; FCEST_OZAKI_SLICES (2..8, default 7) sets the number of 7-bit digits per operand.
+GEMM_IMPL = os.environ.get("FCEST_GEMM_IMPL", "ozaki")
+OZAKI_SLICES = int(os.environ.get("FCEST_OZAKI_SLICES", "7"))
+OZAKI_MIN_FLOPS = 4e9
+
+
+def dgemm_ozaki(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C, alpha=1.0, bias_row=None,
+                slices: int | None = None):
+    """C[:M,:N] = alpha op(A) op(B) (+ bias_row[m]) on the int8 tensor cores; see ``fcest_dgemm_ozaki``."""
+    lib = _lib.load_library()
+    slices = OZAKI_SLICES if slices is None else slices
+    nbytes = int(lib.fcest_dgemm_ozaki_workspace_bytes(M, N, K, slices))
+    if nbytes <= 0:
+        raise ValueError(f"fcest_dgemm_ozaki: unsupported problem M={M} N={N} K={K} slices={slices}")
+    ws = _workspace(nbytes, C.device)
+    call("fcest_dgemm_ozaki", int(a_kmajor), int(b_kmajor), M, N, K, float(alpha), ptr(A), ld(A), ptr(B), ld(B),
+         ptr(C), ld(C), ptr(bias_row), int(slices), ptr(ws), ws.numel() * 8, flops=2.0 * M * N * K)
+    return C
+
+
 def dgemm(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C, alpha=1.0, beta=0.0,
           bias_row=None, bias_col=None):
     """C[:M,:N] = alpha op(A) op(B) + beta C (+ biases); see ``fcest_dgemm`` in the header."""
+    if (GEMM_IMPL == "ozaki" and beta == 0.0 and bias_col is None and 2.0 * M * N * K >= OZAKI_MIN_FLOPS
+            and min(M, N) >= 256 and K >= 512):
+        return dgemm_ozaki(a_kmajor, b_kmajor, M, N, K, A, B, C, alpha=alpha, bias_row=bias_row)
     lib = _lib.load_library()
     nbytes = int(lib.fcest_dgemm_workspace_bytes(M, N, K, ld(C), 1))
     ws = _workspace(nbytes, C.device) if nbytes else None
