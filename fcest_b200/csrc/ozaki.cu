@@ -16,10 +16,12 @@
 // (profiles/r02_ozaki_accuracy_cpu_study.txt).
 //
 // Kernel (persistent, one CTA per SM, 10 warps):
-//   warp 0 (one lane)  TMA producer: per 64-byte K block the B tile set (all digits needed by the pass, two stages)
-//                      and the A tiles (ring of 12), cp.async.bulk.tensor.4d with mbarrier complete_tx
-//   warp 1 (one lane)  MMA issuer: for every (s, t) of the pass two tcgen05.mma (K = 32 each) into the TMEM
-//                      accumulator of order d = s + t; tcgen05.commit releases operand slots / publishes accumulators
+//   warp 0  TMA producer: per 64-byte K block one stage = all A digit tiles and all B digit tiles the pass needs
+//           (28 tile slots of 8 KB handed out FIFO: 2 stages in flight for 7 digits, more for the short second pass),
+//           cp.async.bulk.tensor.4d with mbarrier complete_tx
+//   warp 1  MMA issuer: for every (s, t) of the pass two tcgen05.mma (K = 32 each) into the TMEM accumulator of
+//           order d = s + t; tcgen05.commit releases the stage / publishes the accumulators.  The loop is warp-uniform
+//           and fully unrolled per digit count (descriptors are adds on a base), one elected lane issues
 //   warps 2-9          epilogue: tcgen05.ld of a finished order, int32 -> fp64, Horner step; after the last order
 //                      scale by the row / column exponents and store (or write a split-K partial)
 // All digits of a K block are resident together, so one tile of A_s meets every B_t it pairs with: 10 tile loads per
@@ -40,14 +42,10 @@ namespace oz {
 constexpr int TM = 128, TN = 128;       // output tile
 constexpr int KB = 64;                   // bytes (= int8 elements) of K per staged block
 constexpr int TILE_BYTES = TM * KB;      // 8 KB per digit tile
-constexpr int MAX_NS = 8;
-constexpr int B_STAGES = 2;
-constexpr int A_SLOTS = 12;
+constexpr int MAX_NS = 7;                // digits per operand (all digit tiles of two K blocks must fit shared memory)
 constexpr int NUM_THREADS = 320;         // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int SMEM_B = B_STAGES * MAX_NS * TILE_BYTES;
-constexpr int SMEM_A = A_SLOTS * TILE_BYTES;
 constexpr int SMEM_BAR = 512;
-constexpr int SMEM_TOTAL = SMEM_B + SMEM_A + SMEM_BAR + 1024;  // + alignment slack
+constexpr int SMEM_TOTAL = 28 * TILE_BYTES + SMEM_BAR + 1024;  // 28 tile slots + barriers + alignment slack
 
 struct Params {
   int M, N, tiles_m, tiles_n, nkb, ksplit, ns;
@@ -58,6 +56,7 @@ struct Params {
   double* C;
   long long ldc;
   double* partial;         // ksplit > 1: [ksplit][tiles][128 * 128] unscaled Horner sums
+  long long* dbg;          // optional (FCEST_OZAKI_DEBUG): per-CTA wait-cycle counters, 8 per CTA
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -85,6 +84,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
@@ -138,34 +143,76 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-struct PassInfo {
-  int d_hi, d_lo, nsl;
+// Orders are processed in passes of at most four accumulators: pass 0 covers d = NS-1 .. max(NS-4, 0), pass 1 the rest.
+template <int NS>
+struct Sched {
+  static constexpr int NPASS = NS > 4 ? 2 : 1;
+  __host__ __device__ static constexpr int d_hi(int p) { return p == 0 ? NS - 1 : NS - 5; }
+  __host__ __device__ static constexpr int d_lo(int p) { return p == 0 ? (NS > 4 ? NS - 4 : 0) : 0; }
+  __host__ __device__ static constexpr int nsl(int p) { return d_hi(p) + 1; }   // digits of each operand the pass needs
 };
-__device__ __forceinline__ PassInfo pass_info(int ns, int p) {
-  PassInfo q;
-  q.d_hi = ns - 1 - 4 * p;
-  q.d_lo = q.d_hi - 3 > 0 ? q.d_hi - 3 : 0;
-  q.nsl = q.d_hi + 1;
-  return q;
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
+// Operand staging: NSLOT tile slots of 8 KB handed out FIFO in stages of 2 nsl slots (all A digits, then all B digits
+// of one K block); stage i signals full[i % NBAR] / empty[i % NBAR].  Both the producer and the MMA warp derive the
+// slot positions from the same deterministic sequence.
+constexpr int NSLOT = 28;
+constexpr int NBAR = 8;
+static_assert(NSLOT * TILE_BYTES + SMEM_BAR + 1024 <= 232448, "shared memory budget");
+
+template <int NS, int P>
+__device__ __forceinline__ void mma_stage(uint32_t lo0, uint32_t pos, uint32_t tmem_base, uint32_t first_kb) {
+  using S = Sched<NS>;
+  constexpr int nsl = S::nsl(P), d_hi = S::d_hi(P), d_lo = S::d_lo(P);
+  constexpr uint64_t hi = ((uint64_t)(512 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)4 << 29)) << 32;  // SBO, version, SW64
+  uint32_t b_lo[nsl];
+#pragma unroll
+  for (int t = 0; t < nsl; ++t) {
+    uint32_t slot = pos + nsl + t;
+    slot = slot >= NSLOT ? slot - NSLOT : slot;
+    b_lo[t] = lo0 + slot * (TILE_BYTES >> 4);
+  }
+#pragma unroll
+  for (int s = 0; s < nsl; ++s) {
+    uint32_t slot = pos + s;
+    slot = slot >= NSLOT ? slot - NSLOT : slot;
+    const uint32_t a_lo = lo0 + slot * (TILE_BYTES >> 4);
+#pragma unroll
+    for (int t = 0; t < nsl; ++t) {
+      if (s + t < d_lo || s + t > d_hi) continue;
+      const uint32_t acc = tmem_base + (uint32_t)((d_hi - (s + t)) * TN);
+      const uint32_t keep = s > 0 ? 1u : (first_kb ? 0u : 1u);   // (0, d) is the first product of order d in a unit
+      umma_i8(acc, hi | a_lo, hi | b_lo[t], kInstrDesc, keep);
+      umma_i8(acc, hi | (a_lo + 2), hi | (b_lo[t] + 2), kInstrDesc, 1u);   // second K = 32 step: +32 bytes
+    }
+  }
+}
+
+template <int NS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using S = Sched<NS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smB = base;                  // [stage][digit][8 KB]
-  const uint32_t smA = base + SMEM_B;         // [slot][8 KB]
-  const uint32_t bars = smA + SMEM_A;
-  const uint32_t fullB = bars, emptyB = bars + 16, fullA = bars + 32, emptyA = fullA + 8 * A_SLOTS;
-  const uint32_t tfull = emptyA + 8 * A_SLOTS, tempty = tfull + 32, tptr = tempty + 32;
+  const uint32_t bars = base + NSLOT * TILE_BYTES;
+  const uint32_t full = bars, empty = bars + 8 * NBAR, tfull = empty + 8 * NBAR, tempty = tfull + 32, tptr = tempty + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ns = p.ns, npass = (ns + 3) >> 2;
   const int tiles = p.tiles_m * p.tiles_n;
   const int units = tiles * p.ksplit;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    for (int i = 0; i < A_SLOTS; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
+    for (int i = 0; i < NBAR; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -180,75 +227,106 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+  const bool dbg = p.dbg != nullptr;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      int a_slot = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int ks = u / tiles, tile = u - ks * tiles;
-        const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;
-        const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
-        for (int ps = 0; ps < npass; ++ps) {
-          const PassInfo pi = pass_info(ns, ps);
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(emptyB + 8 * b_stage, b_phase ^ 1u);
-            mbar_expect_tx(fullB + 8 * b_stage, (uint32_t)(pi.nsl * TILE_BYTES));
-            for (int t = 0; t < pi.nsl; ++t)
-              tma_load_4d(smB + (b_stage * MAX_NS + t) * TILE_BYTES, &tmB, fullB + 8 * b_stage, 0, tn * TN, kb, t);
-            if (++b_stage == B_STAGES) { b_stage = 0; b_phase ^= 1u; }
-            for (int s = 0; s < pi.nsl; ++s) {
-              mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1u);
-              mbar_expect_tx(fullA + 8 * a_slot, (uint32_t)TILE_BYTES);
-              tma_load_4d(smA + a_slot * TILE_BYTES, &tmA, fullA + 8 * a_slot, 0, tm * TM, kb, s);
-              if (++a_slot == A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+    // ===================================== TMA producer (warp-uniform loop, one elected lane issues) ==========
+    uint32_t seq = 0, tail = 0, pos = 0, free_slots = NSLOT, sizes = 0;   // sizes: 4 bits per in-flight stage
+    long long w_e = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int ks = u / tiles, tile = u - ks * tiles;
+      const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;
+      const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
+#pragma unroll
+      for (int ps = 0; ps < S::NPASS; ++ps) {
+        const int nsl = S::nsl(ps);
+        const uint32_t n = 2u * nsl;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          while (free_slots < n || seq - tail >= (uint32_t)NBAR) {   // reclaim the oldest stage once the MMAs are done
+            mbar_wait_t(empty + 8 * (tail & (NBAR - 1)), (tail >> 3) & 1u, w_e, dbg);
+            free_slots += (sizes >> (4 * (tail & (NBAR - 1)))) & 15u;
+            ++tail;
+          }
+          const uint32_t sh = 4 * (seq & (NBAR - 1));
+          sizes = (sizes & ~(15u << sh)) | (n << sh);
+          free_slots -= n;
+          if (elect_one()) {
+            const uint32_t fb = full + 8 * (seq & (NBAR - 1));
+            mbar_expect_tx(fb, n * (uint32_t)TILE_BYTES);
+            for (int s = 0; s < nsl; ++s) {
+              uint32_t slot = pos + s;
+              slot = slot >= NSLOT ? slot - NSLOT : slot;
+              tma_load_4d(base + slot * TILE_BYTES, &tmA, fb, 0, tm * TM, kb, s);
+            }
+            for (int t = 0; t < nsl; ++t) {
+              uint32_t slot = pos + nsl + t;
+              slot = slot >= NSLOT ? slot - NSLOT : slot;
+              tma_load_4d(base + slot * TILE_BYTES, &tmB, fb, 0, tn * TN, kb, t);
             }
           }
+          __syncwarp();
+          pos += n;
+          pos = pos >= NSLOT ? pos - NSLOT : pos;
+          ++seq;
         }
       }
     }
-    __syncwarp();
+    if (dbg && lane == 0) {
+      p.dbg[8 * blockIdx.x + 0] = clock64() - t_begin;
+      p.dbg[8 * blockIdx.x + 1] = w_e;
+    }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      int a_slot = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      uint32_t use[4] = {0, 0, 0, 0};  // how often each accumulator has been handed to the epilogue
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int ks = u / tiles;
-        const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
-        for (int ps = 0; ps < npass; ++ps) {
-          const PassInfo pi = pass_info(ns, ps);
-          const int nbuf = pi.d_hi - pi.d_lo + 1;
-          for (int b = 0; b < nbuf; ++b) mbar_wait(tempty + 8 * b, (use[b] & 1u) ^ 1u);  // drained by the epilogue
+    // ===================================== MMA issuer (warp-uniform loop, one elected lane issues) ============
+    uint32_t seq = 0, pos = 0;
+    uint32_t use0 = 0, use1 = 0, use2 = 0, use3 = 0;   // how often each accumulator has been handed to the epilogue
+    long long w_f = 0, w_te = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    const uint32_t lo0 = ((base & 0x3FFFFu) >> 4) | (1u << 16);
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int ks = u / tiles;
+      const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
+#pragma unroll
+      for (int ps = 0; ps < S::NPASS; ++ps) {
+        const int nbuf = S::d_hi(ps) - S::d_lo(ps) + 1;
+        const uint32_t n = 2u * S::nsl(ps);
+        // accumulators of this pass must have been drained by the epilogue
+        if (nbuf > 0) mbar_wait_t(tempty + 0, (use0 & 1u) ^ 1u, w_te, dbg);
+        if (nbuf > 1) mbar_wait_t(tempty + 8, (use1 & 1u) ^ 1u, w_te, dbg);
+        if (nbuf > 2) mbar_wait_t(tempty + 16, (use2 & 1u) ^ 1u, w_te, dbg);
+        if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> 3) & 1u, w_f, dbg);
           tc_fence_after();
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(fullB + 8 * b_stage, b_phase);
-            const uint32_t bset = smB + b_stage * MAX_NS * TILE_BYTES;
-            for (int s = 0; s < pi.nsl; ++s) {
-              mbar_wait(fullA + 8 * a_slot, a_phase);
-              tc_fence_after();
-              const uint64_t da = make_smem_desc(smA + a_slot * TILE_BYTES);
-              const int t_lo = pi.d_lo - s > 0 ? pi.d_lo - s : 0, t_hi = pi.d_hi - s;
-              for (int t = t_lo; t <= t_hi; ++t) {
-                const uint64_t db = make_smem_desc(bset + t * TILE_BYTES);
-                const uint32_t acc = tmem_base + (uint32_t)((pi.d_hi - (s + t)) * TN);
-                const uint32_t keep = (kb > kb0 || s > 0) ? 1u : 0u;  // first product of this order in the unit
-                umma_i8(acc, da, db, kInstrDesc, keep);
-                umma_i8(acc, da + 2, db + 2, kInstrDesc, 1u);         // second K = 32 step: +32 bytes
-              }
-              tc_commit(emptyA + 8 * a_slot);
-              if (++a_slot == A_SLOTS) { a_slot = 0; a_phase ^= 1u; }
-            }
-            tc_commit(emptyB + 8 * b_stage);
-            if (++b_stage == B_STAGES) { b_stage = 0; b_phase ^= 1u; }
+          if (elect_one()) {
+            if (ps == 0) mma_stage<NS, 0>(lo0, pos, tmem_base, kb == kb0);
+            else mma_stage<NS, (S::NPASS > 1 ? 1 : 0)>(lo0, pos, tmem_base, kb == kb0);
+            tc_commit(empty + 8 * (seq & (NBAR - 1)));
           }
-          for (int b = 0; b < nbuf; ++b) { tc_commit(tfull + 8 * b); ++use[b]; }
+          __syncwarp();
+          pos += n;
+          pos = pos >= NSLOT ? pos - NSLOT : pos;
+          ++seq;
         }
+        if (elect_one()) {
+          if (nbuf > 0) tc_commit(tfull + 0);
+          if (nbuf > 1) tc_commit(tfull + 8);
+          if (nbuf > 2) tc_commit(tfull + 16);
+          if (nbuf > 3) tc_commit(tfull + 24);
+        }
+        __syncwarp();
+        if (nbuf > 0) ++use0;
+        if (nbuf > 1) ++use1;
+        if (nbuf > 2) ++use2;
+        if (nbuf > 3) ++use3;
       }
     }
-    __syncwarp();
+    if (dbg && lane == 0) {
+      p.dbg[8 * blockIdx.x + 3] = clock64() - t_begin;
+      p.dbg[8 * blockIdx.x + 4] = w_f;
+      p.dbg[8 * blockIdx.x + 6] = w_te;
+    }
   } else {
     // ===================================== epilogue warps =====================================
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
@@ -258,12 +336,13 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int ks = u / tiles, tile = u - ks * tiles;
       const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;
-      double S[64];
-      bool first = true;
-      for (int ps = 0; ps < npass; ++ps) {
-        const PassInfo pi = pass_info(ns, ps);
-        for (int d = pi.d_hi; d >= pi.d_lo; --d) {
-          const int b = pi.d_hi - d;
+      double acc[64];
+#pragma unroll
+      for (int ps = 0; ps < S::NPASS; ++ps) {
+#pragma unroll
+        for (int d = S::d_hi(ps); d >= S::d_lo(ps); --d) {
+          const int b = S::d_hi(ps) - d;
+          const bool first = ps == 0 && d == S::d_hi(0);
           mbar_wait(tfull + 8 * b, use[b] & 1u);
           tc_fence_after();
 #pragma unroll
@@ -273,17 +352,16 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_wait();
             if (first) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) S[c * 32 + j] = (double)(int)v[j];
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = (double)(int)v[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) S[c * 32 + j] = fma(S[c * 32 + j], 0.0078125, (double)(int)v[j]);
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.0078125, (double)(int)v[j]);
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty + 8 * b);
           ++use[b];
-          first = false;
         }
       }
       const int row = tm * TM + rloc;
@@ -298,20 +376,20 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 64; j += 2) {
               const double2 sc = *reinterpret_cast<const double2*>(p.rsB + col0 + j);
               double2 o;
-              o.x = S[j] * sr * sc.x + br;
-              o.y = S[j + 1] * sr * sc.y + br;
+              o.x = acc[j] * sr * sc.x + br;
+              o.y = acc[j + 1] * sr * sc.y + br;
               *reinterpret_cast<double2*>(crow + col0 + j) = o;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 64; ++j)
-              if (col0 + j < p.N) crow[col0 + j] = S[j] * sr * p.rsB[col0 + j] + br;
+              if (col0 + j < p.N) crow[col0 + j] = acc[j] * sr * p.rsB[col0 + j] + br;
           }
         }
       } else {
         double* dst = p.partial + ((long long)ks * tiles + tile) * (TM * TN) + rloc * TN + half * 64;
 #pragma unroll
-        for (int j = 0; j < 64; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(S[j], S[j + 1]);
+        for (int j = 0; j < 64; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(acc[j], acc[j + 1]);
       }
     }
   }
@@ -491,6 +569,8 @@ static int make_map(CUtensorMap* map, void* base, int rows_pad, int nkb, int ns)
   return r == CUDA_SUCCESS ? 0 : FCEST_ERR_ARGUMENT;
 }
 
+static long long* g_debug_counters = nullptr;
+
 static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 struct Plan {
@@ -556,10 +636,26 @@ static int split_operand(const double* X, long long ld, int kmajor, int rows, in
   return 0;
 }
 
+template <int NS>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  ozaki_gemm_kernel<NS><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  FCEST_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace oz
 }  // namespace fcest
 
 using namespace fcest;
+
+// diagnostics: device buffer of 8 counters per CTA filled by the next GEMM launches (null = off)
+extern "C" void fcest_dgemm_ozaki_debug(long long* counters) { oz::g_debug_counters = counters; }
 
 extern "C" long long fcest_dgemm_ozaki_workspace_bytes(int M, int N, int K, int slices) {
   if (M < 1 || N < 1 || K < 1 || slices < 2 || slices > oz::MAX_NS) return 0;
@@ -594,16 +690,19 @@ extern "C" int fcest_dgemm_ozaki(int a_kmajor, int b_kmajor, int M, int N, int K
   p.M = M; p.N = N; p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.nkb = pl.nkb; p.ksplit = pl.ksplit; p.ns = slices;
   p.alpha = alpha; p.rsA = rsA; p.rsB = rsB; p.bias_row = bias_row; p.C = C; p.ldc = ldc;
   p.partial = (double*)(ws + pl.off_part);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_TOTAL);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  p.dbg = oz::g_debug_counters;
   const int units = pl.tiles_m * pl.tiles_n * pl.ksplit;
   const int grid = units < sms ? units : sms;
-  oz::ozaki_gemm_kernel<<<grid, oz::NUM_THREADS, oz::SMEM_TOTAL, stream>>>(tmA, tmB, p);
-  FCEST_CHECK_LAUNCH();
+  rc = FCEST_ERR_ARGUMENT;
+  switch (slices) {
+    case 2: rc = oz::launch_gemm<2>(tmA, tmB, p, grid, stream); break;
+    case 3: rc = oz::launch_gemm<3>(tmA, tmB, p, grid, stream); break;
+    case 4: rc = oz::launch_gemm<4>(tmA, tmB, p, grid, stream); break;
+    case 5: rc = oz::launch_gemm<5>(tmA, tmB, p, grid, stream); break;
+    case 6: rc = oz::launch_gemm<6>(tmA, tmB, p, grid, stream); break;
+    case 7: rc = oz::launch_gemm<7>(tmA, tmB, p, grid, stream); break;
+  }
+  if (rc) return rc;
   if (pl.ksplit > 1) {
     oz::ozaki_fixup_kernel<<<dim3(pl.tiles_m * pl.tiles_n, 16), 256, 0, stream>>>(p);
     FCEST_CHECK_LAUNCH();

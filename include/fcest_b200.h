@@ -62,10 +62,9 @@ int fcest_dgemm(int a_kmajor, int b_kmajor, int M, int N, int K, double alpha, c
                 cudaStream_t stream);
 
 /* ---- the same GEMM on the int8 tensor cores (tcgen05.mma kind::i8 + TMEM + TMA): Ozaki-style emulation of
- *      C = alpha op(A) op(B) + bias_row[m]  (beta = 0, no batch).  Operand rows are cut into `slices` (2..8) signed
+ *      C = alpha op(A) op(B) + bias_row[m]  (beta = 0, no batch).  Operand rows are cut into `slices` (2..7) signed
  *      7-bit digits; digit pairs with s + t < slices are exact integer GEMMs; error <= (slices + 1) K 2^(-7 slices)
- *      relative to max|A_m| max|B_n| (slices = 7: ~1e-12 of the largest entry at the C4 shapes, slices = 8: below the
- *      rounding of a native fp64 GEMM).  Used for the three projection GEMMs of SVGP.elbo / predict_f
+ *      relative to max|A_m| max|B_n| (slices = 7: ~1e-12 of the largest entry at the C4 shapes).  Used for the three projection GEMMs of SVGP.elbo / predict_f
  *      (fcest/models/wishart_process.py:381-386 -> gpflow base_conditional).  Deterministic (fixed-order sums).
  *      workspace: fcest_dgemm_ozaki_workspace_bytes(M, N, K, slices) bytes of device memory. */
 long long fcest_dgemm_ozaki_workspace_bytes(int M, int N, int K, int slices);
@@ -73,6 +72,10 @@ int fcest_dgemm_ozaki(int a_kmajor, int b_kmajor, int M, int N, int K, double al
                       long long lda, const double* B, long long ldb, double* C, long long ldc,
                       const double* bias_row, int slices, void* workspace, long long workspace_bytes,
                       cudaStream_t stream);
+
+/*      diagnostics: while `counters` (8 x #SM long long, device) is non-null every launch records per-CTA wait cycles
+ *      of the producer and MMA roles there. */
+void fcest_dgemm_ozaki_debug(long long* counters);
 
 /* ---- packed quadratic-form projection (replaces the (R,M,N) LTA tensor of base_conditional and its
  *      autodiff).  K = M(M+1)/2 packed lower-triangle entries, row pitch ldk >= K, even.

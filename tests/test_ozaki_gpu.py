@@ -57,7 +57,7 @@ def test_ozaki_matches_fp64_matmul(cuda, M, N, K, a_kmajor, b_kmajor):
     assert rel < 1e-11
 
 
-@pytest.mark.parametrize("slices", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("slices", [2, 3, 4, 5, 6, 7])
 def test_ozaki_slice_counts_follow_the_error_model(cuda, slices):
     A, B = _operands(200, 333, 1500, True, True, seed=slices)
     C = _run(A, B, True, True, slices)
