@@ -38,6 +38,12 @@ LIK_KERNEL_NAME = "wishart_loglik_warp_kernel<7> (+ 2 colsum reductions)"
 # capture (a constant from the named profile, NOT measured in the bench run)
 TRAFFIC_BYTES_PER_LAUNCH = 777e6
 TRAFFIC_SOURCE = "constant from profiles/r01_ncu_summary.md (ncu --set full of the round-1 build: 969 / 604 / 758 MB for V, Gk, Tk); not measured in this run"
+# int8-emulated GEMM: DRAM traffic of the GEMM kernel from the ncu --set full capture named below; algorithmic bytes =
+# digit arrays read once (7 x (1280 + 2560) x 20160 B) + the fp64 partial / output tiles written once
+OZAKI_TRAFFIC_BYTES_PER_LAUNCH = 976e6
+OZAKI_TRAFFIC_SOURCE = ("constant from profiles/r02_ncu_ozaki.md (ncu --set full, V = Pk Sk^T: dram read 622 MB + write 354 MB); "
+                        "not measured in this run")
+OZAKI_ALGORITHMIC_BYTES = 7 * (1280 + 2560) * 20160 + 5 * 200 * 128 * 128 * 8
 CPU_ARM_BUDGET_S = 200.0   # wall-clock budget of the --impl reference run (full-size evaluations only)
 
 
@@ -154,6 +160,24 @@ def measure_fp64_peak(dev):
             best = min(best, e0.elapsed_time(e1))
     del a, b, c
     return 2.0 * n ** 3 / (best * 1e-3) * 1e-12
+
+
+def measure_int8_peak(dev):
+    """Issue-rate ceiling of the int8 tensor pipe measured in this run: back-to-back tcgen05.mma kind::i8 (128x128x32, 64
+    cycles each) on every SM for ~0.7 ms, CUDA events, best of 5 (the power state of a real GEMM is not reproduced: zero
+    operands).  MEASURED_PEAKS.json only has a bf16 figure; the int8 pipe is nominally twice as wide."""
+    from fcest_b200 import _lib
+    lib = _lib.load_library()
+    best = 0.0
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops_issued = int(lib.fcest_int8_mma_peak(20000, _lib.stream(dev)))
+        e1.record()
+        torch.cuda.synchronize()
+        if ops_issued > 0 and i >= 2:
+            best = max(best, ops_issued / (e0.elapsed_time(e1) * 1e-3) * 1e-12)
+    return best
 
 
 def strong_scaling_block(dev, rank, world, K, single_gpu_ms):
@@ -379,6 +403,11 @@ def run_cuda(args):
     _cond.OVERLAP_BACKWARD = False
     step((x_dev, y_dev))
     torch.cuda.synchronize()
+    from fcest_b200 import ops as _ops
+    use_ozaki = _ops.GEMM_IMPL == "ozaki"
+    lib = _lib.load_library()
+    if use_ozaki:
+        lib.fcest_dgemm_ozaki_profile(1)   # event pair around the GEMM kernel proper inside every fcest_dgemm_ozaki call
     _lib.PROFILE = {"min_flops": 1e10, "records": []}
     for _ in range(K):
         step((x_dev, y_dev))
@@ -386,9 +415,16 @@ def run_cuda(args):
     records = _lib.PROFILE["records"]
     _lib.PROFILE = None
     _cond.OVERLAP_BACKWARD = True
-    gemm_ms = [r[2].elapsed_time(r[3]) for r in records]
+    gemm_ms = [r[2].elapsed_time(r[3]) for r in records]     # whole call (digit extraction + GEMM kernel + split-K sum)
     gemm_fl = [r[1] for r in records]
     gemm_tflops = sum(gemm_fl) / (sum(gemm_ms) * 1e-3) * 1e-12 if gemm_ms else 0.0
+    kern_ms = []
+    if use_ozaki:
+        import ctypes as _C
+        buf = (_C.c_float * 512)()
+        n = int(lib.fcest_dgemm_ozaki_profile_read(buf, 512))
+        lib.fcest_dgemm_ozaki_profile(0)
+        kern_ms = [float(buf[i]) for i in range(max(n, 0))]
 
     # ---- end-to-end: public API with HOST (pinned) inputs, ELBO read back every step --------------
     barrier()
@@ -449,6 +485,7 @@ def run_cuda(args):
 
     # ---- fp64 roofline denominator measured in this run; strong-scaling leg (N > 1) ----------------------------
     peak_measured = measure_fp64_peak(dev) if rank == 0 else None
+    int8_peak = measure_int8_peak(dev) if (rank == 0 and use_ozaki) else None
     del model
     torch.cuda.empty_cache()
     strong = strong_scaling_block(dev, rank, world, K, t_ms / K) if world > 1 else None
@@ -457,12 +494,54 @@ def run_cuda(args):
         peak_file = json.load(open(FP64_PEAK_FILE))["fp64_tflops"] if os.path.exists(FP64_PEAK_FILE) else None
         peak = peak_measured
         lik_ms = per.get("fcest_wishart_loglik", 0.0)
+        flops_gemm = flops["projection"] / 3.0
+        if use_ozaki:
+            ns = _ops.OZAKI_SLICES
+            pairs = ns * (ns + 1) // 2
+            k_ms = float(np.mean(kern_ms)) if kern_ms else float("nan")
+            mb = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops") \
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+            achieved = pairs * flops_gemm / (k_ms * 1e-3) * 1e-12
+            roofline = {
+                "bound": "tensor",
+                "kernel": f"ozaki_gemm_kernel<{ns}> (tcgen05.mma kind::i8, TMEM accumulators, TMA-staged digit tiles): the 3 "
+                          "projection GEMMs per step, each an fp64 GEMM emulated by %d exact int8 digit-pair GEMMs" % pairs,
+                "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak if int8_peak else None,
+                "unit_note": "int8 tensor operations (multiply + add) per second, i.e. TOP/s; algorithmic = digit pairs x 2 N R K, "
+                             "tile padding (1200 -> 1280, 2500 -> 2560, 20100 -> 20160) not counted",
+                "algorithmic_int8_ops_per_launch": pairs * flops_gemm, "digit_pairs": pairs, "digits": ns,
+                "kernel_ms": k_ms, "launches_timed": len(kern_ms),
+                "peak_source": "measured in THIS run: back-to-back tcgen05.mma kind::i8 128x128x32 on all SMs (fcest_int8_mma_peak, "
+                               "64 cycles per instruction), CUDA events, best of 5; MEASURED_PEAKS.json has no int8 figure",
+                "peak_alt_2x_measured_bf16": 2.0 * mb if mb else None,
+                "traffic": OZAKI_TRAFFIC_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch", "traffic_source": OZAKI_TRAFFIC_SOURCE,
+                "algorithmic_bytes_per_launch": OZAKI_ALGORITHMIC_BYTES,
+                "fp64_equivalent": {
+                    "what": "the fp64 GEMM each call replaces (2 N R K flop) over the duration of the WHOLE call (digit extraction "
+                            "+ GEMM kernel + split-K sum), against the fp64 tensor peak measured in this run",
+                    "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "ratio": gemm_tflops / peak,
+                    "call_ms": float(np.mean(gemm_ms)) if gemm_ms else None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul, best of 10, CUDA events, this run"},
+                "how": "CUDA event pair recorded by the library around every GEMM kernel launch (fcest_dgemm_ozaki_profile), "
+                       "in a separate pass of the same K steps with the two backward chains serialised on one stream"}
+        else:
+            roofline = {"bound": "tensor", "kernel": GEMM_KERNEL_NAME + " (3 projection GEMMs per step)",
+                        "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
+                        "traffic": TRAFFIC_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch", "traffic_source": TRAFFIC_SOURCE,
+                        "algorithmic_bytes_per_launch": 619e6,
+                        "peak_source": "measured in THIS run on this GPU: cuBLAS DGEMM 8192^3 via torch.matmul, best of "
+                                       "10, CUDA events (MEASURED_PEAKS.json has no fp64 figure)",
+                        "algorithmic_flops_per_launch": flops_gemm, "launches_timed": len(gemm_ms),
+                        "how": "CUDA events around every projection GEMM launch in a separate pass of the same K steps "
+                               "with the two backward chains serialised on one stream"}
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": K, "warmup": warm_steps, "warmup_requested": args.warmup,
             "ms_per_step": t_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD,
+                       "gemm": ("projection GEMMs: fp64 emulated on the int8 tensor cores, %d digits (error ~1e-12 of the largest "
+                                "entry); everything else native fp64" % _ops.OZAKI_SLICES) if use_ozaki else "native fp64 (DMMA)",
                        "sharding": "one independent C4 subject per GPU (replicas; ELBO sum all-reduced)",
                        "l2": "per-step working set 2.8 GB (q_sqrt, Sk, Pk, Gk, Tk, eps) >> 126 MB L2, no flush needed",
                        "rng": "fresh Philox N(0,1) draw per step, generated on device inside the step"},
@@ -470,20 +549,10 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(x_pin.numel() * 8 + y_pin.numel() * 8),
                     "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": GEMM_KERNEL_NAME + " (3 projection GEMMs per step)",
-                         "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch",
-                         "traffic_source": TRAFFIC_SOURCE,
-                         "algorithmic_bytes_per_launch": 619e6,
-                         "peak_source": "measured in THIS run on this GPU: cuBLAS DGEMM 8192^3 via torch.matmul, best of "
-                                        "10, CUDA events (MEASURED_PEAKS.json has no fp64 figure)",
-                         "peak_builder_file": peak_file,
-                         "algorithmic_flops_per_launch": flops["projection"] / 3.0,
-                         "launches_timed": len(gemm_ms),
-                         "how": "CUDA events around every projection GEMM launch in a separate pass of the same K steps "
-                                "with the two backward chains serialised on one stream; in the timed region two of the "
-                                "three GEMMs overlap on two streams"},
-            "roofline_step": {"algorithmic_flops": sum(flops.values()),
+            "roofline": roofline,
+            "roofline_step": {"note": "algorithmic fp64 flops of the whole evaluation over the step time, against the fp64 peak; "
+                                      "above 1 when the projection GEMMs run on the int8 tensor pipe",
+                              "algorithmic_flops": sum(flops.values()),
                               "achieved": sum(flops.values()) / (t_ms / K * 1e-3) * 1e-12, "peak": peak,
                               "unit": "TFLOP/s", "frac": sum(flops.values()) / (t_ms / K * 1e-3) * 1e-12 / peak},
             "roofline_likelihood": {"kernel": LIK_KERNEL_NAME, "ms": lik_ms,

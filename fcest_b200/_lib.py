@@ -32,6 +32,9 @@ SIGNATURES = {
     "fcest_dgemm_ozaki_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "fcest_dgemm_ozaki": (_i, [_i, _i, _i, _i, _i, _d, _p, _ll, _p, _ll, _p, _ll, _p, _i, _p, _ll, _p]),
     "fcest_dgemm_ozaki_debug": (None, [_p]),
+    "fcest_dgemm_ozaki_profile": (_i, [_i]),
+    "fcest_dgemm_ozaki_profile_read": (_i, [_p, _i]),
+    "fcest_int8_mma_peak": (_ll, [_i, _p]),
     "fcest_pack_outer": (_i, [_p, _ll, _i, _i, _p, _ll, _p, _p, _i, _p]),
     "fcest_tri_syrk_pack": (_i, [_p, _i, _i, _p, _ll, _p, _p]),
     "fcest_tri_grad": (_i, [_p, _ll, _p, _i, _i, _p, _d, _p]),

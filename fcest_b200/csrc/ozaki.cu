@@ -636,6 +636,14 @@ static int split_operand(const double* X, long long ld, int kmajor, int rows, in
   return 0;
 }
 
+// Measurement hook (bench.py): while enabled, every call records a pair of CUDA events around its GEMM kernel launch
+// on the caller's stream; fcest_dgemm_ozaki_profile_read synchronises them and returns the durations.
+constexpr int PROF_MAX = 512;
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[PROF_MAX][2];
+static bool g_prof_created = false;
+
 template <int NS>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
@@ -644,15 +652,89 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Par
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  const bool prof = g_prof_on && g_prof_n < PROF_MAX;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], stream);
   ozaki_gemm_kernel<NS><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], stream);
   FCEST_CHECK_LAUNCH();
   return 0;
+}
+
+// Back-to-back tcgen05.mma kind::i8 (M 128, N 128, K 32) on zero operands: the issue-rate ceiling of the int8 tensor pipe
+// (64 cycles per instruction, tools/microbench/umma_rate.cu); bench.py times it with CUDA events as the roofline peak.
+__global__ void __launch_bounds__(128, 1) int8_mma_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tptr_s;
+  __shared__ __align__(8) uint64_t bar_s;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < 4 * TILE_BYTES / 4; i += blockDim.x)
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4 * i), "r"(0) : "memory");
+  const uint32_t bar = smem_u32(&bar_s), tptr = smem_u32(&tptr_s);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+  if (threadIdx.x < 32) {
+    const uint64_t da = make_smem_desc(base), db = make_smem_desc(base + 2 * TILE_BYTES);
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) umma_i8(tmem_base + (uint32_t)((i & 3) * TN), da + 2 * (i & 1), db + 2 * (i & 1), kInstrDesc, 1u);
+      tc_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
 }
 
 }  // namespace oz
 }  // namespace fcest
 
 using namespace fcest;
+
+extern "C" int fcest_dgemm_ozaki_profile(int enable) {
+  if (enable && !oz::g_prof_created) {
+    for (int i = 0; i < oz::PROF_MAX; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (cudaEventCreate(&oz::g_prof_ev[i][j]) != cudaSuccess) return FCEST_ERR_UNSUPPORTED;
+    oz::g_prof_created = true;
+  }
+  oz::g_prof_on = enable != 0;
+  if (enable) oz::g_prof_n = 0;
+  return 0;
+}
+
+extern "C" int fcest_dgemm_ozaki_profile_read(float* ms, int max_n) {
+  int n = oz::g_prof_n < max_n ? oz::g_prof_n : max_n;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(oz::g_prof_ev[i][1]) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(&ms[i], oz::g_prof_ev[i][0], oz::g_prof_ev[i][1]) != cudaSuccess) return -1;
+  }
+  return n;
+}
+
+extern "C" long long fcest_int8_mma_peak(int iters, cudaStream_t stream) {
+  const int smem = 4 * oz::TILE_BYTES + 1024;
+  const int sms = oz::sm_count();
+  oz::int8_mma_peak_kernel<<<sms, 128, smem, stream>>>(iters);
+  fcest_launch_count_add(1);
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  return (long long)sms * iters * 2LL * oz::TM * oz::TN * 32;   // int8 operations issued
+}
 
 // diagnostics: device buffer of 8 counters per CTA filled by the next GEMM launches (null = off)
 extern "C" void fcest_dgemm_ozaki_debug(long long* counters) { oz::g_debug_counters = counters; }

@@ -73,6 +73,14 @@ int fcest_dgemm_ozaki(int a_kmajor, int b_kmajor, int M, int N, int K, double al
                       const double* bias_row, int slices, void* workspace, long long workspace_bytes,
                       cudaStream_t stream);
 
+/*      measurement hooks (bench.py; the only entry points that create CUDA events or synchronise): with profiling
+ *      enabled every fcest_dgemm_ozaki call records an event pair around its GEMM kernel on the caller's stream;
+ *      _profile_read waits for them and returns up to max_n kernel durations in milliseconds (count, or -1).
+ *      fcest_int8_mma_peak launches back-to-back tcgen05.mma kind::i8 on every SM (the issue-rate ceiling of the
+ *      int8 tensor pipe) and returns the number of int8 operations it issues: time it with events for the roofline. */
+int fcest_dgemm_ozaki_profile(int enable);
+int fcest_dgemm_ozaki_profile_read(float* ms, int max_n);
+long long fcest_int8_mma_peak(int iters, cudaStream_t stream);
 /*      diagnostics: while `counters` (8 x #SM long long, device) is non-null every launch records per-CTA wait cycles
  *      of the producer and MMA roles there. */
 void fcest_dgemm_ozaki_debug(long long* counters);
