@@ -7,13 +7,15 @@
 // though ns (ns + 1) / 2 integer GEMMs replace one fp64 GEMM.
 //
 // Arithmetic.  Every operand row (a vector along the contraction axis) is scaled by a power of two into (-1, 1) and
-// cut into ns balanced base-128 digits q_s in [-64, 64]:   x = 2^e sum_s q_s 2^(-6 - 7 s)   (exact operations: power-
-// of-two scaling, rint, subtraction).  The product keeps the digit pairs with s + t < ns:
-//     C[i][j] = 2^(eA_i + eB_j - 12) sum_{d < ns} 2^(-7 d) sum_{s + t = d} (A_s B_t^T)[i][j]
-// Each inner sum is an EXACT integer GEMM (|q| <= 64, int32 accumulation, at most 8 pairs x 65536 terms per
+// cut into ns balanced base-254 digits q_s in [-127, 127] (the full int8 range: 7.99 bits per digit):
+//     x = 2^e / 127 * sum_s q_s 254^(-s),     q_0 = rint(127 x / 2^e),  q_{s+1} = rint(254 (t_s - q_s))
+// (the remainder t_s - q_s is exact; the multiplication by 254 rounds at 2^-53, far below the last digit).  The product
+// keeps the digit pairs with s + t < ns:
+//     C[i][j] = 2^(eA_i + eB_j) / 127^2 * sum_{d < ns} 254^(-d) sum_{s + t = d} (A_s B_t^T)[i][j]
+// Each inner sum is an EXACT integer GEMM (|q| <= 127, int32 accumulation, at most 7 pairs x 16384 terms per
 // accumulator); the sum over d runs in fp64, least significant order first (Horner).  Dropped terms are bounded by
-// (ns + 1) K 2^(-7 ns) relative to max|A_i| max|B_j| -- measured at C4: 6e-13 of the largest entry for ns = 7
-// (profiles/r02_ozaki_accuracy_cpu_study.txt).
+// (ns + 1) K 254^(-ns) relative to max|A_i| max|B_j|: ns = 6 carries 47.9 bits (measured at C4: ~1e-12 of the largest
+// entry), ns = 7 carries 55.9 bits, more than the fp64 operands hold.
 //
 // Kernel (persistent, one CTA per SM, 10 warps):
 //   warp 0  TMA producer: per 64-byte K block one stage = all A digit tiles and all B digit tiles the pass needs
@@ -355,7 +357,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               for (int j = 0; j < 32; ++j) acc[c * 32 + j] = (double)(int)v[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.0078125, (double)(int)v[j]);
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 1.0 / 254.0, (double)(int)v[j]);
             }
           }
           tc_fence_before();
@@ -428,12 +430,14 @@ __global__ void __launch_bounds__(256) ozaki_fixup_kernel(const Params p) {
 // ---------------------------------------------------------------------------------------------------------------
 // digit extraction
 // ---------------------------------------------------------------------------------------------------------------
-// biased exponent field E of max|x| -> (input scale 2^(6 - e), output scale 2^(e - 6)), e = E - 1022; zero / tiny rows -> 0
+// biased exponent field E of max|x| -> (input scale 2^-e, output scale 2^e / 127), e = E - 1022 so that |x| 2^-e < 1;
+// zero / tiny rows -> 0.  The first digit is rint(127 x 2^-e).
 __device__ __forceinline__ void scales_from_exp(uint32_t E, double& s_in, double& s_out) {
   if (E < 8u || E > 2040u) { s_in = 0.0; s_out = 0.0; return; }
-  s_in = __longlong_as_double((long long)(2051u - E) << 52);
-  s_out = __longlong_as_double((long long)(E - 5u) << 52);
+  s_in = __longlong_as_double((long long)(2045u - E) << 52);                     // 2^-(E - 1022)
+  s_out = __longlong_as_double((long long)(E + 1u) << 52) * (1.0 / 127.0);       // 2^(E - 1022) / 127
 }
+constexpr double kDigitBase = 254.0, kFirstDigit = 127.0;
 
 // Operand stored with the contraction axis contiguous: X (rows, Kc), row pitch ld.  One CTA per (padded) output row.
 // out[((s * nkb + kb) * rows_pad + row) * 64 + k % 64]
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
   for (int k8 = tid * 8; k8 < Kp; k8 += 256 * 8) {
     double t[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = (live && k8 + i < Kc) ? x[k8 + i] * s_in : 0.0;
+    for (int i = 0; i < 8; ++i) t[i] = (live && k8 + i < Kc) ? (x[k8 + i] * s_in) * kFirstDigit : 0.0;
     const int kb = k8 >> 6;
     int8_t* dst = out + ((long long)kb * rows_pad + row) * KB + (k8 & 63);
     for (int s = 0; s < ns; ++s) {
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const double qd = rint(t[i]);
-        t[i] = (t[i] - qd) * 128.0;
+        t[i] = (t[i] - qd) * kDigitBase;
         const uint32_t b = (uint32_t)((int)qd) & 0xFFu;
         if (i < 4) lo |= b << (8 * i); else hi |= b << (8 * (i - 4));
       }
@@ -512,14 +516,14 @@ __global__ void __launch_bounds__(256) split_cols_kernel(const double* __restric
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = kb * 64 + 4 * g + i;
-      t[i] = (j < cols && k < Kc) ? X[(long long)k * ld + j] * s_in : 0.0;
+      t[i] = (j < cols && k < Kc) ? (X[(long long)k * ld + j] * s_in) * kFirstDigit : 0.0;
     }
     for (int s = 0; s < ns; ++s) {
       uint32_t w = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const double qd = rint(t[i]);
-        t[i] = (t[i] - qd) * 128.0;
+        t[i] = (t[i] - qd) * kDigitBase;
         w |= ((uint32_t)((int)qd) & 0xFFu) << (8 * i);
       }
       tile[s][tx][g] = w;
@@ -586,9 +590,9 @@ static Plan make_plan(int M, int N, int K, int ns, int sms) {
   pl.tiles_n = pl.Np / TN;
   pl.nkb = (int)((K + KB - 1) / KB);
   const int tiles = pl.tiles_m * pl.tiles_n;
-  // K split: fewest splits within 3 % of the best wave efficiency; every unit keeps >= 8 K blocks and at most 1024
-  // (int32 accumulators: 8 pairs x 65536 terms x 64^2 < 2^31)
-  int ks_min = (pl.nkb + 1023) / 1024, best = ks_min;
+  // K split: fewest splits within 3 % of the best wave efficiency; every unit keeps >= 8 K blocks and at most 256
+  // (int32 accumulators: 7 pairs x 16384 terms x 127^2 < 2^31)
+  int ks_min = (pl.nkb + 255) / 256, best = ks_min;
   double best_cost = 1e300;
   for (int ks = ks_min; ks <= 16; ++ks) {
     if (ks > ks_min && pl.nkb / ks < 8) break;

@@ -56,9 +56,9 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 
 # Large GEMMs go to the int8 tensor cores (tcgen05 Ozaki-style emulation, ``fcest_dgemm_ozaki``) unless
-# FCEST_GEMM_IMPL=dmma; FCEST_OZAKI_SLICES (2..8, default 7) sets the number of 7-bit digits per operand.
+# FCEST_GEMM_IMPL=dmma; FCEST_OZAKI_SLICES (2..7, default 6 = 47.9 bits) sets the number of base-254 digits per operand.
 GEMM_IMPL = os.environ.get("FCEST_GEMM_IMPL", "ozaki")
-OZAKI_SLICES = int(os.environ.get("FCEST_OZAKI_SLICES", "7"))
+OZAKI_SLICES = int(os.environ.get("FCEST_OZAKI_SLICES", "6"))
 OZAKI_MIN_FLOPS = 4e9
 
 

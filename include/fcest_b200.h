@@ -62,9 +62,9 @@ int fcest_dgemm(int a_kmajor, int b_kmajor, int M, int N, int K, double alpha, c
                 cudaStream_t stream);
 
 /* ---- the same GEMM on the int8 tensor cores (tcgen05.mma kind::i8 + TMEM + TMA): Ozaki-style emulation of
- *      C = alpha op(A) op(B) + bias_row[m]  (beta = 0, no batch).  Operand rows are cut into `slices` (2..7) signed
- *      7-bit digits; digit pairs with s + t < slices are exact integer GEMMs; error <= (slices + 1) K 2^(-7 slices)
- *      relative to max|A_m| max|B_n| (slices = 7: ~1e-12 of the largest entry at the C4 shapes).  Used for the three projection GEMMs of SVGP.elbo / predict_f
+ *      C = alpha op(A) op(B) + bias_row[m]  (beta = 0, no batch).  Operand rows are cut into `slices` (2..7) balanced
+ *      base-254 digits (int8); digit pairs with s + t < slices are exact integer GEMMs; error <= (slices + 1) K 254^-slices
+ *      relative to max|A_m| max|B_n| (slices = 6: 47.9 bits, ~1e-12 of the largest entry at the C4 shapes; 7: 55.9 bits).  Used for the three projection GEMMs of SVGP.elbo / predict_f
  *      (fcest/models/wishart_process.py:381-386 -> gpflow base_conditional).  Deterministic (fixed-order sums).
  *      workspace: fcest_dgemm_ozaki_workspace_bytes(M, N, K, slices) bytes of device memory. */
 long long fcest_dgemm_ozaki_workspace_bytes(int M, int N, int K, int slices);

@@ -1,6 +1,6 @@
 """fcest_dgemm_ozaki (fp64 GEMM emulated on the int8 tensor cores: tcgen05.mma kind::i8, TMEM, TMA) against torch's
-float64 matmul.  The error model of the scheme (ozaki.cu header): with ns 7-bit digits per operand row,
-|C - C_ref|[i][j] <= (ns + 2) K 2^(-7 ns) (2 max|A_i|) (2 max|B_j|)  (+ fp64 rounding of the reference itself)."""
+float64 matmul.  The error model of the scheme (ozaki.cu header): with ns base-254 digits per operand row,
+|C - C_ref|[i][j] <= (ns + 2) K 254^(-ns) (2 max|A_i|) (2 max|B_j|)  (+ fp64 rounding of the reference itself)."""
 import numpy as np
 import pytest
 import torch
@@ -37,7 +37,7 @@ def _check(C, A, B, slices, alpha=1.0, bias=None):
     ref = alpha * (A @ B.t())
     if bias is not None:
         ref = ref + bias[:, None]
-    bound = (slices + 2) * K * 2.0 ** (-7 * slices) * (2 * A.abs().amax(1))[:, None] * (2 * B.abs().amax(1))[None, :]
+    bound = (slices + 2) * K * 254.0 ** (-slices) * (2 * A.abs().amax(1))[:, None] * (2 * B.abs().amax(1))[None, :]
     bound = abs(alpha) * bound + 1e-15 * K ** 0.5 * (A.abs().amax(1)[:, None] * B.abs().amax(1)[None, :]) * abs(alpha) + 1e-300
     bound = bound + 4e-16 * ref.abs()   # rounding of the bias addition / the final scaling
     err = (C - ref).abs()
@@ -52,9 +52,11 @@ def _check(C, A, B, slices, alpha=1.0, bias=None):
 @pytest.mark.parametrize("a_kmajor,b_kmajor", [(True, True), (False, False), (True, False), (False, True)])
 def test_ozaki_matches_fp64_matmul(cuda, M, N, K, a_kmajor, b_kmajor):
     A, B = _operands(M, N, K, a_kmajor, b_kmajor, seed=M + N + K)
-    C = _run(A, B, a_kmajor, b_kmajor, 7)
-    rel = _check(C, A, B, 7)
-    assert rel < 1e-11
+    C = _run(A, B, a_kmajor, b_kmajor, 6)
+    rel = _check(C, A, B, 6)
+    assert rel < 1e-10
+    C = _run(A, B, a_kmajor, b_kmajor, 7)   # 55.9 bits: only the rounding of the two fp64 results is left
+    assert _check(C, A, B, 7) < 1e-12
 
 
 @pytest.mark.parametrize("slices", [2, 3, 4, 5, 6, 7])
@@ -80,7 +82,7 @@ def test_ozaki_split_k_path_and_determinism(cuda):
     C1 = _run(A, B, True, True, 7)
     C2 = _run(A, B, True, True, 7)
     assert torch.equal(C1, C2)
-    assert _check(C1, A, B, 7) < 1e-11
+    assert _check(C1, A, B, 7) < 1e-12
 
 
 def test_ozaki_projection_shapes_match_dmma(cuda):
@@ -103,6 +105,6 @@ def test_ozaki_projection_shapes_match_dmma(cuda):
             ops.dgemm(*args, ref, **kw)
         finally:
             ops.GEMM_IMPL = impl
-        ops.dgemm_ozaki(*args, got, slices=7, **kw)
+        ops.dgemm_ozaki(*args, got, slices=6, **kw)
         rel = float((got - ref).abs().max() / ref.abs().max())
-        assert rel < 1e-11, (args[:5], rel)
+        assert rel < 1e-10, (args[:5], rel)
