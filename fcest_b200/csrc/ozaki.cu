@@ -1,5 +1,5 @@
 // fp64 GEMM on the 5th-generation tensor cores: Ozaki-style int8-slice emulation (tcgen05.mma kind::i8, int32
-// accumulators in TMEM, operand tiles staged by TMA).
+// accumulators in TMEM, operand tiles staged by TMA bulk copies).
 //
 // Why: the three projection GEMMs  V = Pk Sk^T,  Gk = g^T Pk,  Tk = g Sk   are 98 % of
 // the flops of an ELBO + gradient evaluation and the native fp64 tensor path (DMMA, 37 TFLOP/s) has no tcgen05 form.
@@ -20,7 +20,8 @@
 // Kernel (persistent, one CTA per SM, 10 warps):
 //   warp 0  TMA producer: per 64-byte K block one stage = all A digit tiles and all B digit tiles the pass needs
 //           (28 tile slots of 8 KB handed out FIFO: 2 stages in flight for 7 digits, more for the short second pass),
-//           cp.async.bulk.tensor.4d with mbarrier complete_tx
+//           cp.async.bulk (the digit arrays are stored pre-swizzled tile by tile: a tile is one contiguous 8 KB copy; 64-byte
+//           rows fetched through a tensor map ran at half the L2 -> shared-memory rate), mbarrier complete_tx
 //   warp 1  MMA issuer: for every (s, t) of the pass two tcgen05.mma (K = 32 each) into the TMEM accumulator of
 //           order d = s + t; tcgen05.commit releases the stage / publishes the accumulators.  The loop is warp-uniform
 //           and fully unrolled per digit count (descriptors are adds on a base), one elected lane issues
@@ -31,7 +32,6 @@
 // orders are processed in passes of four (d = ns-1 .. ns-4, then the rest).
 // Work units = (K split, 128 x 128 output tile), dealt round-robin to the CTAs in K-split-major order so that
 // concurrently running CTAs stream the same K range (the digit arrays of one K split stay L2 resident).
-#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -58,6 +58,8 @@ struct Params {
   double* C;
   long long ldc;
   double* partial;         // ksplit > 1: [ksplit][tiles][128 * 128] unscaled Horner sums
+  const int8_t* dA;        // digit tiles of op(A): [digit][K block][tiles_m * 128 rows][64 B], each 128-row tile pre-swizzled
+  const int8_t* dB;        // digit tiles of op(B)
   long long* dbg;          // optional (FCEST_OZAKI_DEBUG): per-CTA wait-cycle counters, 8 per CTA
 };
 
@@ -93,13 +95,16 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long 
   mbar_wait(bar, parity);
   acc += clock64() - t0;
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
+// 1-D bulk copy (TMA engine, SASS UBLKCP): one contiguous 8 KB digit tile global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
 }
+// position of byte b (0..63) of row r inside a 128-row x 64-byte tile in the 64-byte swizzle the MMA descriptor names:
+// the 16-byte chunk index is XORed with bits 1-2 of the row.  The digit arrays are stored pre-swizzled, so a tile is a
+// plain contiguous copy.
+__host__ __device__ __forceinline__ int swz64(int r, int b) { return r * KB + ((((b >> 4) ^ (r >> 1)) & 3) << 4) + (b & 15); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -203,7 +208,7 @@ __device__ __forceinline__ void mma_stage(uint32_t lo0, uint32_t pos, uint32_t t
 
 template <int NS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+ozaki_gemm_kernel(const Params p) {
   using S = Sched<NS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -217,8 +222,6 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < NBAR; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512) : "memory");
@@ -256,15 +259,18 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (elect_one()) {
             const uint32_t fb = full + 8 * (seq & (NBAR - 1));
             mbar_expect_tx(fb, n * (uint32_t)TILE_BYTES);
+            const long long strideA = (long long)p.nkb * p.tiles_m * TM * KB, strideB = (long long)p.nkb * p.tiles_n * TN * KB;
+            const int8_t* srcA = p.dA + ((long long)kb * p.tiles_m + tm) * TILE_BYTES;
+            const int8_t* srcB = p.dB + ((long long)kb * p.tiles_n + tn) * TILE_BYTES;
             for (int s = 0; s < nsl; ++s) {
               uint32_t slot = pos + s;
               slot = slot >= NSLOT ? slot - NSLOT : slot;
-              tma_load_4d(base + slot * TILE_BYTES, &tmA, fb, 0, tm * TM, kb, s);
+              bulk_load(base + slot * TILE_BYTES, srcA + s * strideA, TILE_BYTES, fb);
             }
             for (int t = 0; t < nsl; ++t) {
               uint32_t slot = pos + nsl + t;
               slot = slot >= NSLOT ? slot - NSLOT : slot;
-              tma_load_4d(base + slot * TILE_BYTES, &tmB, fb, 0, tn * TN, kb, t);
+              bulk_load(base + slot * TILE_BYTES, srcB + t * strideB, TILE_BYTES, fb);
             }
           }
           __syncwarp();
@@ -440,7 +446,7 @@ __device__ __forceinline__ void scales_from_exp(uint32_t E, double& s_in, double
 constexpr double kDigitBase = 254.0, kFirstDigit = 127.0;
 
 // Operand stored with the contraction axis contiguous: X (rows, Kc), row pitch ld.  One CTA per (padded) output row.
-// out[((s * nkb + kb) * rows_pad + row) * 64 + k % 64]
+// out[((s * nkb + kb) * rows_pad + 128 (row / 128)) * 64 + swz64(row % 128, k % 64)]
 __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restrict__ X, long long ld, int rows, int Kc,
                                                          int rows_pad, int nkb, int ns, int8_t* __restrict__ out,
                                                          double* __restrict__ rs) {
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = (live && k8 + i < Kc) ? (x[k8 + i] * s_in) * kFirstDigit : 0.0;
     const int kb = k8 >> 6;
-    int8_t* dst = out + ((long long)kb * rows_pad + row) * KB + (k8 & 63);
+    int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & 63);
     for (int s = 0; s < ns; ++s) {
       uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -535,7 +541,8 @@ __global__ void __launch_bounds__(256) split_cols_kernel(const double* __restric
     const int s = c / 256, rem = c - s * 256, col = rem >> 2, part = rem & 3;
     const uint32_t* src = &tile[s][col][part * 4];
     const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
-    int8_t* dst = out + (((long long)s * nkb + kb) * cols_pad + blockIdx.x * 64 + col) * KB + part * 16;
+    const int orow = blockIdx.x * 64 + col;
+    int8_t* dst = out + (((long long)s * nkb + kb) * cols_pad + (orow & ~127)) * KB + swz64(orow & 127, part * 16);
     *reinterpret_cast<uint4*>(dst) = v;
   }
 }
@@ -543,36 +550,6 @@ __global__ void __launch_bounds__(256) split_cols_kernel(const double* __restric
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
-        qr == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
-// digits[s][kb][row][64 bytes]  ->  rank-4 map, box = one 128-row x 64-byte tile, 64-byte swizzle
-static int make_map(CUtensorMap* map, void* base, int rows_pad, int nkb, int ns) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return FCEST_ERR_UNSUPPORTED;
-  const cuuint64_t dims[4] = {(cuuint64_t)KB, (cuuint64_t)rows_pad, (cuuint64_t)nkb, (cuuint64_t)ns};
-  const cuuint64_t strides[3] = {(cuuint64_t)KB, (cuuint64_t)rows_pad * KB, (cuuint64_t)nkb * rows_pad * KB};
-  const cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)TM, 1, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : FCEST_ERR_ARGUMENT;
-}
-
 static long long* g_debug_counters = nullptr;
 
 static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
@@ -649,7 +626,7 @@ static cudaEvent_t g_prof_ev[PROF_MAX][2];
 static bool g_prof_created = false;
 
 template <int NS>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p, int grid, cudaStream_t stream) {
+static int launch_gemm(const Params& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
@@ -658,7 +635,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Par
   }
   const bool prof = g_prof_on && g_prof_n < PROF_MAX;
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], stream);
-  ozaki_gemm_kernel<NS><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  ozaki_gemm_kernel<NS><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(p);
   if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], stream);
   FCEST_CHECK_LAUNCH();
   return 0;
@@ -767,26 +744,23 @@ extern "C" int fcest_dgemm_ozaki(int a_kmajor, int b_kmajor, int M, int N, int K
   if (rc) return rc;
   rc = oz::split_operand(B, ldb, b_kmajor, N, K, pl.Np, pl.nkb, slices, dB, rsB, Etmp, stream);
   if (rc) return rc;
-  CUtensorMap tmA, tmB;
-  rc = oz::make_map(&tmA, dA, pl.Mp, pl.nkb, slices);
-  if (rc) return rc;
-  rc = oz::make_map(&tmB, dB, pl.Np, pl.nkb, slices);
-  if (rc) return rc;
   oz::Params p;
   p.M = M; p.N = N; p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.nkb = pl.nkb; p.ksplit = pl.ksplit; p.ns = slices;
   p.alpha = alpha; p.rsA = rsA; p.rsB = rsB; p.bias_row = bias_row; p.C = C; p.ldc = ldc;
   p.partial = (double*)(ws + pl.off_part);
+  p.dA = dA;
+  p.dB = dB;
   p.dbg = oz::g_debug_counters;
   const int units = pl.tiles_m * pl.tiles_n * pl.ksplit;
   const int grid = units < sms ? units : sms;
   rc = FCEST_ERR_ARGUMENT;
   switch (slices) {
-    case 2: rc = oz::launch_gemm<2>(tmA, tmB, p, grid, stream); break;
-    case 3: rc = oz::launch_gemm<3>(tmA, tmB, p, grid, stream); break;
-    case 4: rc = oz::launch_gemm<4>(tmA, tmB, p, grid, stream); break;
-    case 5: rc = oz::launch_gemm<5>(tmA, tmB, p, grid, stream); break;
-    case 6: rc = oz::launch_gemm<6>(tmA, tmB, p, grid, stream); break;
-    case 7: rc = oz::launch_gemm<7>(tmA, tmB, p, grid, stream); break;
+    case 2: rc = oz::launch_gemm<2>(p, grid, stream); break;
+    case 3: rc = oz::launch_gemm<3>(p, grid, stream); break;
+    case 4: rc = oz::launch_gemm<4>(p, grid, stream); break;
+    case 5: rc = oz::launch_gemm<5>(p, grid, stream); break;
+    case 6: rc = oz::launch_gemm<6>(p, grid, stream); break;
+    case 7: rc = oz::launch_gemm<7>(p, grid, stream); break;
   }
   if (rc) return rc;
   if (pl.ksplit > 1) {
