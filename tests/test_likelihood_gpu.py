@@ -122,3 +122,77 @@ def test_warp_and_cta_kernels_agree(cuda):
     for k in ("ve", "g_fmean", "g_fvar", "gA", "glam"):
         a, b = outs[0][k], outs[1][k]
         assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max(), k
+
+
+# D above the shared-memory tile store (208 <= D <= 400; the reference takes any D, likelihoods.py:185)
+@pytest.mark.parametrize("D", [256, 320, 400])
+def test_loglik_large_D(cuda, D):
+    _check(N=2, D=D, S=2, seed=D)
+
+
+def test_large_D_prediction_and_pd_check(cuda):
+    """predict moments and the batched PD check at D = 256 and 400 against the oracle."""
+    from fcest_b200 import ops
+    from fcest_b200.helpers.array_operations import are_all_positive_definite
+    for D, n, S in ((256, 2, 3), (400, 1, 2)):
+        rng = np.random.default_rng(D)
+        t = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64)
+        fm, fv = t(0.3 * rng.standard_normal((n, D * D))), t(0.05 + rng.random((n, D * D)))
+        A, lam = t(np.eye(D) + 0.1 * rng.standard_normal((D, D))), t(wo.inv_softplus(0.01) + 0.1 * rng.standard_normal(D))
+        eps = t(rng.standard_normal((S, n, D, D)))
+        for corr, fn in ((0, wo.predict_cov), (1, wo.predict_corr)):
+            mean_ref, std_ref = fn(fm, fv, A, lam, eps, D)
+            dev = "cuda"
+            mean = torch.empty((n, D, D), dtype=torch.float64, device=dev)
+            m2 = torch.empty_like(mean); out_mean = torch.empty_like(mean); out_std = torch.empty_like(mean)
+            from fcest_b200 import _lib
+            nscr = int(_lib.load_library().fcest_cov_moments_scratch_bytes(D, D))
+            scratch = torch.empty(max(nscr // 8, 1), dtype=torch.float64, device=dev)
+            fmd, fvd = ops.as_pitched(fm.cuda()), ops.as_pitched(fv.cuda())
+            eps_d, A_d, lam_d = eps.reshape(S, n, D * D).cuda().contiguous(), A.cuda(), lam.cuda()   # keep alive
+            ops.call("fcest_cov_moments", ops.ptr(fmd), ops.ptr(fvd), ops.ld(fmd), ops.ptr(eps_d),
+                     ops.ptr(A_d), 0, ops.ptr(lam_d), S, n, D, D, corr, 0, ops.ptr(mean), ops.ptr(m2), None, 1,
+                     ops.ptr(out_mean), ops.ptr(out_std), ops.ptr(scratch))
+            torch.cuda.synchronize()
+            assert _rel(out_mean, mean_ref) < 1e-9 and _rel(out_std, std_ref) < 1e-8, (D, corr)
+            if not corr:
+                assert are_all_positive_definite(out_mean)
+                bad = out_mean.clone()
+                bad[0] -= 2.0 * torch.linalg.eigvalsh(bad[0].cpu()).max().item() * torch.eye(D, dtype=torch.float64, device=dev)
+                assert not are_all_positive_definite(bad)
+
+
+def test_kernels_are_run_to_run_deterministic(cuda):
+    """No atomics on the data path and fixed-order reductions: five runs of the likelihood (warp and tile kernels),
+    of the per-latent triangular kernels (shared work counter) and of the window covariance (two-buffer bulk store)
+    give bit-identical outputs -- the race evidence available here (compute-sanitizer is closed on this pool)."""
+    from fcest_b200 import ops
+    from fcest_b200.models import SlidingWindows
+    for D, N, S in ((50, 40, 8), (72, 6, 3)):
+        fmean, fvar, y, A, lam, eps = _inputs(N, D, S, 3)
+        args = (ops.as_pitched(fmean.cuda()), ops.as_pitched(fvar.cuda()), eps.cuda(), y.cuda(), A.cuda(), lam.cuda())
+        ref = ops.wishart_loglik(*args)
+        for _ in range(4):
+            out = ops.wishart_loglik(*args)
+            for k in ("ve", "g_fmean", "g_fvar", "gA", "glam"):
+                assert torch.equal(out[k], ref[k]), (D, k)
+    g = torch.Generator().manual_seed(0)
+    R, M = 300, 200
+    ldk = (M * (M + 1) // 2 + 15) // 16 * 16
+    q = torch.tril(torch.randn(R, M, M, dtype=torch.float64, generator=g)).cuda().contiguous()
+    Gk = torch.randn(R, ldk, dtype=torch.float64, generator=g).cuda()
+    outs = []
+    for _ in range(5):
+        Sk = torch.empty((R, ldk), dtype=torch.float64, device="cuda")
+        klp = torch.empty((R, 2), dtype=torch.float64, device="cuda")
+        dq = torch.empty_like(q)
+        ops.call("fcest_tri_syrk_pack", ops.ptr(q), R, M, ops.ptr(Sk), ldk, ops.ptr(klp))
+        ops.call("fcest_tri_grad", ops.ptr(Gk), ldk, ops.ptr(q), R, M, ops.ptr(dq), 1.0)
+        outs.append((Sk[:, :M * (M + 1) // 2].clone(), klp, dq))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(o, outs[0]))
+    y = np.random.default_rng(1).standard_normal((1200, 100))
+    sw = SlidingWindows(np.linspace(0, 1, 1200)[:, None], y)
+    first = sw.overlapping_windowed_cov_estimation(30)
+    for _ in range(4):
+        assert np.array_equal(sw.overlapping_windowed_cov_estimation(30), first)
