@@ -35,6 +35,16 @@ class Parameter:
 
     # -- tf.Variable / gpflow.Parameter surface -------------------------------------------------
     def assign(self, value) -> None:
+        if isinstance(value, torch.Tensor) and value.is_cuda and self.transform in (None, "tril"):
+            # device-resident value (e.g. the 0.8 GB q_sqrt of a D = 200 subject): no host round trip
+            t = value.detach().to(device=self.device, dtype=F64)
+            t = torch.tril(t) if self.transform == "tril" else t.clone()
+            t = t.contiguous()
+            if self.unconstrained is not None and self.unconstrained.shape == t.shape:
+                self.unconstrained.copy_(t)
+            else:
+                self.unconstrained = t
+            return
         v = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
         v = np.array(v, dtype=np.float64)
         if self.transform == "softplus":

@@ -117,6 +117,51 @@ class GraphedTrainingStep:
             self.model._check_chol(info[1])
 
 
+class GraphedEvaluation:
+    """One ELBO + gradient evaluation captured in a CUDA graph (``model.compile_evaluation``)."""
+
+    def __init__(self, model, data):
+        self.model = model
+        self.x, self.y = model._data(data)
+        lik = model.likelihood
+        self.eps = torch.empty((lik.num_mc_samples, self.y.shape[0], lik.D * lik.nu), dtype=torch.float64,
+                               device=self.y.device)
+        self.graph, self.elbo, self.calls = None, None, 0
+
+    def __call__(self, epsilon=None) -> torch.Tensor:
+        lik = self.model.likelihood
+        if epsilon is None:
+            ops.randn(self.eps, lik._seed, lik._draws)
+            lik._draws += 1
+        else:
+            self.eps.copy_(epsilon.reshape(self.eps.shape))
+        if self.calls == 0:      # eager: warm-up of allocator / lazy module loads
+            self.elbo = self.model.elbo_and_grad((self.x, self.y), epsilon=self.eps, check=False)
+        elif self.calls == 1:
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.elbo = self.model.elbo_and_grad((self.x, self.y), epsilon=self.eps, check=False)
+            # the graph writes its results into these tensors on every replay
+            self._grads = [(p, p.grad) for p in self.model.parameters]
+            self._info = self.model._last_info
+            self.graph.replay()
+        else:
+            self.graph.replay()
+        if self.graph is not None:   # an eager evaluation in between may have re-pointed Parameter.grad
+            for p, g in self._grads:
+                p.grad = g
+            self.model._last_info = self._info
+        self.calls += 1
+        return self.elbo
+
+    def check(self) -> None:
+        info = getattr(self.model, "_last_info", None)
+        if info is not None:
+            self.model.likelihood.check_info(info[0])
+            self.model._check_chol(info[1])
+
+
 def run_adam(
     model_type: str,
     model,

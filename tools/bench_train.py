@@ -45,11 +45,31 @@ def run(cfg, graphed, iters=200, fuse=True):
     return iters / dt, float(e.item())
 
 
+def run_eval(cfg, graphed, iters=200):
+    """ELBO + gradient evaluations per second (no optimiser): eager launches vs model.compile_evaluation."""
+    m, data = build(cfg)
+    if graphed:
+        f = m.compile_evaluation(data)
+        step = lambda: f()
+    else:
+        xd_yd = m._data(data)
+        step = lambda: m.elbo_and_grad(xd_yd, check=False)
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    torch.cuda.synchronize()
+    return iters / (time.perf_counter() - t0)
+
+
 res = {}
 for cfg in ("C1", "C2"):
     eager, _ = run(cfg, False)
     graph, _ = run(cfg, True)
-    res[cfg] = {"eager_it_per_s": eager, "cuda_graph_it_per_s": graph, "speedup": graph / eager}
+    res[cfg] = {"eager_it_per_s": eager, "cuda_graph_it_per_s": graph, "speedup": graph / eager,
+                "eval_eager_per_s": run_eval(cfg, False), "eval_cuda_graph_per_s": run_eval(cfg, True)}
 unfused, _ = run("C4", True, iters=40, fuse=False)
 fused, _ = run("C4", True, iters=40, fuse=True)
 res["C4"] = {"cuda_graph_it_per_s_unfused_adam": unfused, "cuda_graph_it_per_s_fused_q_sqrt_adam": fused,
