@@ -75,13 +75,18 @@ class SubjectBatch:
             self.data.append(d)
         self.optimizers = [optimizer_factory(m) for m in self.models] if optimizer_factory else None
 
-    def step(self, device=None) -> torch.Tensor:
+    def step(self, device=None, keep_grads: bool = True) -> torch.Tensor:
+        """``keep_grads=False`` drops every subject's gradients once its optimiser (if any) has consumed them: with
+        many resident subjects the dense q_sqrt gradients (8 M^2 R bytes each) would otherwise double the footprint."""
         total = None
         for i, (m, d) in enumerate(zip(self.models, self.data)):
             e = m.elbo_and_grad(d, check=False).reshape(1)
             total = e.clone() if total is None else total + e
             if self.optimizers is not None:
                 self.optimizers[i].step()
+            if not keep_grads:
+                for prm in m.parameters:
+                    prm.grad = None
         if total is None:
             total = torch.zeros(1, dtype=torch.float64, device=device or "cpu")
         return allreduce_sum_(total)

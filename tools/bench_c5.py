@@ -47,6 +47,8 @@ def main():
     t_build = time.perf_counter() - t_build
     # warm-up: one evaluation of the first local subject (module loads, allocator, workspaces), not a full sweep
     batch.models[0].elbo_and_grad(batch.data[0], check=False)
+    for prm in batch.models[0].parameters:
+        prm.grad = None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -54,7 +56,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        total = batch.step(dev)
+        total = batch.step(dev, keep_grads=False)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / a.steps], dtype=torch.float64, device=dev)
