@@ -154,7 +154,7 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
     if OVERLAP_BACKWARD:
         side.wait_stream(main)
     with torch.cuda.stream(chain_stream):
-        ops.dgemm(False, False, R, K, N, g_fvar, st.Pk, Gk)
+        ops.dgemm(False, False, R, K, N, g_fvar, st.Pk, Gk, backward=True)
         if gk_reduce is not None:
             gk_reduce(Gk)
         if fuse:
@@ -168,7 +168,7 @@ def conditional_backward(st: CondState, g_fmean, g_fvar, need_Z: bool, with_kl: 
 
     # T_n (packed) = g_var Sk  ->  dP = 2 T_n p_n (- prior term)
     Tk = torch.empty((N, ldk), dtype=F64, device=dev)
-    ops.dgemm(True, False, N, K, R, g_fvar, st.Sk, Tk)
+    ops.dgemm(True, False, N, K, R, g_fvar, st.Sk, Tk, backward=True)
     dP = ops.pitched(M, N, dev)
     gs = torch.empty(N, dtype=F64, device=dev)
     ops.call("fcest_sym_matvec", ops.ptr(Tk), ldk, ops.ptr(st.P), ops.ld(st.P), M, N, ops.ptr(g_fvar),

@@ -57,8 +57,11 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 # Large GEMMs go to the int8 tensor cores (tcgen05 Ozaki-style emulation, ``fcest_dgemm_ozaki``) unless
 # FCEST_GEMM_IMPL=dmma; FCEST_OZAKI_SLICES (2..7, default 6 = 47.9 bits) sets the number of base-254 digits per operand.
+# The two backward GEMMs (gradients, held to 1e-7 relative-to-max) use FCEST_OZAKI_SLICES_BWD digits (default 5 = 39.9
+# bits: ~3e-11 of the largest entry).
 GEMM_IMPL = os.environ.get("FCEST_GEMM_IMPL", "ozaki")
 OZAKI_SLICES = int(os.environ.get("FCEST_OZAKI_SLICES", "6"))
+OZAKI_SLICES_BWD = int(os.environ.get("FCEST_OZAKI_SLICES_BWD", "5"))
 OZAKI_MIN_FLOPS = 4e9
 
 
@@ -77,11 +80,13 @@ def dgemm_ozaki(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C,
 
 
 def dgemm(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C, alpha=1.0, beta=0.0,
-          bias_row=None, bias_col=None):
-    """C[:M,:N] = alpha op(A) op(B) + beta C (+ biases); see ``fcest_dgemm`` in the header."""
+          bias_row=None, bias_col=None, backward: bool = False):
+    """C[:M,:N] = alpha op(A) op(B) + beta C (+ biases); see ``fcest_dgemm`` in the header.  ``backward`` marks a
+    gradient GEMM (fewer digits on the int8 path)."""
     if (GEMM_IMPL == "ozaki" and beta == 0.0 and bias_col is None and 2.0 * M * N * K >= OZAKI_MIN_FLOPS
             and min(M, N) >= 256 and K >= 512):
-        return dgemm_ozaki(a_kmajor, b_kmajor, M, N, K, A, B, C, alpha=alpha, bias_row=bias_row)
+        return dgemm_ozaki(a_kmajor, b_kmajor, M, N, K, A, B, C, alpha=alpha, bias_row=bias_row,
+                           slices=OZAKI_SLICES_BWD if backward else OZAKI_SLICES)
     lib = _lib.load_library()
     nbytes = int(lib.fcest_dgemm_workspace_bytes(M, N, K, ld(C), 1))
     ws = _workspace(nbytes, C.device) if nbytes else None
