@@ -483,6 +483,38 @@ def run_cuda(args):
                 "frac": wbytes / wms * 1e-6 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)"}
         del yw, ow, flush
 
+    # ---- the small BASELINE configurations (launch-bound): ELBO + gradient evaluations/s through the CUDA-graph
+    #      evaluation (model.compile_evaluation), outside the timed region, rank 0 at N = 1 only ------------------
+    small = None
+    if rank == 0 and world == 1:
+        small = {}
+        from fcest_b200.helpers.synthetic import make_synthetic
+        from fcest_b200.models import SparseVariationalWishartProcess, VariationalWishartProcess
+        for name, (n_, d_, s_, m_) in {"C1: VWP N=200 D=3 S=5": (200, 3, 5, None), "C2: SVWP N=1200 D=15 M=200 S=3": (1200, 15, 3, 200)}.items():
+            q = make_synthetic(n_, d_, s_, M=m_, seed=0, want_eps=False)
+            if m_ is None:
+                mm = VariationalWishartProcess(q["x"], q["y"], num_mc_samples=s_, device=dev)
+                data = None
+            else:
+                mm = SparseVariationalWishartProcess(d_, q["Z"], num_mc_samples=s_, verbose=False, device=dev)
+                data = (q["x"], q["y"])
+            mm.q_mu.assign(q["q_mu"]); mm.q_sqrt.assign(q["q_sqrt"])
+            mm.likelihood.A_scale_matrix.assign(q["A"]); mm.likelihood.additive_part.assign(q["lam"])
+            f = mm.compile_evaluation(data)
+            for _ in range(5):
+                f()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(100):
+                f()
+            b.record()
+            torch.cuda.synchronize()
+            f.check()
+            small[name] = {"evals_per_s": 100.0 / (a.elapsed_time(b) * 1e-3), "ms_per_eval": a.elapsed_time(b) / 100.0,
+                           "how": "100 CUDA-graph evaluations (one graph launch + one Philox launch each), CUDA events"}
+            del mm, f
+
     # ---- fp64 roofline denominator measured in this run; strong-scaling leg (N > 1) ----------------------------
     peak_measured = measure_fp64_peak(dev) if rank == 0 else None
     int8_peak = measure_int8_peak(dev) if (rank == 0 and use_ozaki) else None
@@ -570,6 +602,8 @@ def run_cuda(args):
         }
         if strong is not None:
             line["strong"] = strong
+        if small is not None:
+            line["small_configs"] = small
         if world == 1 and not args.no_cpu_baseline:
             # CPU baseline + parity at the metric's own configuration: the SAME epsilon goes through the CPU
             # restatement and through the CUDA path (fresh model at the same seed), ELBO and every gradient compared

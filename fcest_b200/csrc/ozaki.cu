@@ -6,16 +6,15 @@
 // The int8 tensor pipe is ~100x wider, so an error-bounded split of the fp64 operands into 7-bit digits wins even
 // though ns (ns + 1) / 2 integer GEMMs replace one fp64 GEMM.
 //
-// Arithmetic.  Every operand row (a vector along the contraction axis) is scaled by a power of two into (-1, 1) and
-// cut into ns balanced base-254 digits q_s in [-127, 127] (the full int8 range: 7.99 bits per digit):
-//     x = 2^e / 127 * sum_s q_s 254^(-s),     q_0 = rint(127 x / 2^e),  q_{s+1} = rint(254 (t_s - q_s))
-// (the remainder t_s - q_s is exact; the multiplication by 254 rounds at 2^-53, far below the last digit).  The product
-// keeps the digit pairs with s + t < ns:
-//     C[i][j] = 2^(eA_i + eB_j) / 127^2 * sum_{d < ns} 254^(-d) sum_{s + t = d} (A_s B_t^T)[i][j]
-// Each inner sum is an EXACT integer GEMM (|q| <= 127, int32 accumulation, at most 7 pairs x 16384 terms per
-// accumulator); the sum over d runs in fp64, least significant order first (Horner).  Dropped terms are bounded by
-// (ns + 1) K 254^(-ns) relative to max|A_i| max|B_j|: ns = 6 carries 47.9 bits (measured at C4: ~1e-12 of the largest
-// entry), ns = 7 carries 55.9 bits, more than the fp64 operands hold.
+// Arithmetic.  Every operand row (a vector along the contraction axis) is scaled by a power of two into (-1, 1), rounded
+// once to a signed fixed-point integer of 8 ns - 2 bits and read as ns balanced base-256 digits d_s in [-128, 127]
+// (the bytes of (X + 0x80..80) XOR 0x80..80; no per-digit arithmetic):   x = 2^(e - 6) sum_s d_s 256^-s.
+// The product keeps the digit pairs with s + t < ns:
+//     C[i][j] = 2^(eA_i + eB_j - 12) sum_{d < ns} 256^-d sum_{s + t = d} (A_s B_t^T)[i][j]
+// Each inner sum is an EXACT integer GEMM (|d| <= 128, int32 accumulation, at most 7 pairs x 16384 terms per
+// accumulator); the sum over d runs in fp64, least significant order first (Horner; the factor 1/256 is exact).
+// Error <= 4 (ns + 2) K 256^-ns relative to max|A_i| max|B_j| (operand rounding + dropped pairs): ns = 5 / 6 / 7 carry
+// 38 / 46 / 54 bits per operand (7: every fp64 operand is represented exactly).
 //
 // Kernel (persistent, one CTA per SM, 10 warps):
 //   warp 0  TMA producer: per 64-byte K block one stage = all A digit tiles and all B digit tiles the pass needs
@@ -363,7 +362,7 @@ ozaki_gemm_kernel(const Params p) {
               for (int j = 0; j < 32; ++j) acc[c * 32 + j] = (double)(int)v[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 1.0 / 254.0, (double)(int)v[j]);
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.00390625, (double)(int)v[j]);
             }
           }
           tc_fence_before();
@@ -419,10 +418,19 @@ __global__ void __launch_bounds__(256) ozaki_fixup_kernel(const Params p) {
   const int row = tm * TM + rloc;
   if (row >= p.M) return;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int ks = 0; ks < p.ksplit; ++ks) {
-    const double* src = p.partial + ((long long)ks * tiles + tile) * (TM * TN) + rloc * TN + cloc;
-    const double2 a = *reinterpret_cast<const double2*>(src), b = *reinterpret_cast<const double2*>(src + 2);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+  const double* src0 = p.partial + (long long)tile * (TM * TN) + rloc * TN + cloc;
+  const long long kstride = (long long)tiles * (TM * TN);
+  for (int ks0 = 0; ks0 < p.ksplit; ks0 += 4) {   // four splits in flight, summed in split order
+    double2 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool on = ks0 + u < p.ksplit;
+      const double* src = src0 + (ks0 + u) * kstride;
+      a[u] = on ? *reinterpret_cast<const double2*>(src) : make_double2(0.0, 0.0);
+      b[u] = on ? *reinterpret_cast<const double2*>(src + 2) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += b[u].x; acc[3] += b[u].y; }
   }
   const double sr = p.rsA[row] * p.alpha;
   const double br = p.bias_row ? p.bias_row[row] : 0.0;
@@ -436,14 +444,40 @@ __global__ void __launch_bounds__(256) ozaki_fixup_kernel(const Params p) {
 // ---------------------------------------------------------------------------------------------------------------
 // digit extraction
 // ---------------------------------------------------------------------------------------------------------------
-// biased exponent field E of max|x| -> (input scale 2^-e, output scale 2^e / 127), e = E - 1022 so that |x| 2^-e < 1;
-// zero / tiny rows -> 0.  The first digit is rint(127 x 2^-e).
-__device__ __forceinline__ void scales_from_exp(uint32_t E, double& s_in, double& s_out) {
-  if (E < 8u || E > 2040u) { s_in = 0.0; s_out = 0.0; return; }
-  s_in = __longlong_as_double((long long)(2045u - E) << 52);                     // 2^-(E - 1022)
-  s_out = __longlong_as_double((long long)(E + 1u) << 52) * (1.0 / 127.0);       // 2^(E - 1022) / 127
+// Digits.  A row is scaled by a power of two into (-1, 1) and rounded ONCE to a signed fixed-point integer of 8 ns - 2 bits,
+//     X = rint(x 2^(8 ns - 2 - e)),   |X| <= 2^(8 ns - 2),
+// whose balanced base-256 digits d_s in [-128, 127] (top digit |d_0| <= 65) are read off as BYTES: with C = 0x80..80,
+// X = (X + C) - C = sum_i (u_i - 128) 256^i for the unsigned bytes u_i of X + C, and u - 128 as an int8 is u XOR 0x80, so the
+// bytes of Z = (X + C) XOR C are the digits.  No per-digit arithmetic: one multiply, one rounding, two integer ops per
+// element, then a byte transpose.  x = 2^(e - 6) sum_s d_s 256^-s.
+// biased exponent field E of max|x| -> (input scale 2^(8 ns - 2 - e), output scale 2^(e - 6)), e = E - 1022; zero / tiny
+// rows -> 0.
+__device__ __forceinline__ void scales_from_exp(uint32_t E, int ns, double& s_in, double& s_out) {
+  if (E < 64u || E > 1980u) { s_in = 0.0; s_out = 0.0; return; }
+  s_in = __longlong_as_double((long long)(2043u + 8u * (uint32_t)ns - E) << 52);
+  s_out = __longlong_as_double((long long)(E - 5u) << 52);
 }
-constexpr double kDigitBase = 254.0, kFirstDigit = 127.0;
+__device__ __forceinline__ unsigned long long digits_of(double x, double s_in, int ns) {
+  const double v = x * s_in;   // exact (power of two)
+  long long X;
+  if (ns <= 6) {   // |v| <= 2^46: round to nearest even through the 1.5 2^52 trick (full-rate fp64 add)
+    X = __double_as_longlong(v + 6755399441055744.0) - 0x4338000000000000LL;
+  } else {
+    X = __double2ll_rn(v);
+  }
+  const unsigned long long C = 0x8080808080808080ULL;
+  return ((unsigned long long)X + C) ^ C;   // byte i (little endian) = digit of weight 256^i
+}
+// byte `p` (0..7) of four 64-bit words -> one 32-bit word (word i in byte i)
+__device__ __forceinline__ uint32_t gather_byte(const unsigned long long (&z)[4], int p) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = p < 4 ? (uint32_t)z[i] : (uint32_t)(z[i] >> 32);
+  const uint32_t q = (uint32_t)(p & 3);
+  const uint32_t a = __byte_perm(w[0], w[1], q | ((4u + q) << 4));        // bytes [w0.q, w1.q, -, -]
+  const uint32_t b = __byte_perm(w[2], w[3], q | ((4u + q) << 4));
+  return __byte_perm(a, b, 0x5410);                                         // [w0.q, w1.q, w2.q, w3.q]
+}
 
 // Operand stored with the contraction axis contiguous: X (rows, Kc), row pitch ld.  One CTA per (padded) output row.
 // out[((s * nkb + kb) * rows_pad + 128 (row / 128)) * 64 + swz64(row % 128, k % 64)]
@@ -456,9 +490,20 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
   const double* x = X + (long long)row * ld;
   uint32_t E = 0;
   if (live) {
-    for (int k = tid; k < Kc; k += 256) {
-      const uint32_t e = ((uint32_t)(__double_as_longlong(x[k]) >> 52)) & 0x7FFu;
-      E = e > E ? e : E;
+    const bool vec = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    if (vec) {   // 16-byte loads, two per thread in flight
+      const int K2 = Kc >> 1;
+      const double2* x2 = reinterpret_cast<const double2*>(x);
+      for (int k = tid; k < K2; k += 512) {
+        const double2 a = x2[k];
+        const double2 b = (k + 256 < K2) ? x2[k + 256] : make_double2(0.0, 0.0);
+        const uint32_t e0 = ((uint32_t)(__double_as_longlong(a.x) >> 52)) & 0x7FFu, e1 = ((uint32_t)(__double_as_longlong(a.y) >> 52)) & 0x7FFu;
+        const uint32_t e2 = ((uint32_t)(__double_as_longlong(b.x) >> 52)) & 0x7FFu, e3 = ((uint32_t)(__double_as_longlong(b.y) >> 52)) & 0x7FFu;
+        E = max(max(E, max(e0, e1)), max(e2, e3));
+      }
+      if ((Kc & 1) && tid == 0) E = max(E, ((uint32_t)(__double_as_longlong(x[Kc - 1]) >> 52)) & 0x7FFu);
+    } else {
+      for (int k = tid; k < Kc; k += 256) E = max(E, ((uint32_t)(__double_as_longlong(x[k]) >> 52)) & 0x7FFu);
     }
   }
 #pragma unroll
@@ -469,25 +514,93 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
 #pragma unroll
   for (int w = 1; w < 8; ++w) E = redE[w] > E ? redE[w] : E;
   double s_in, s_out;
-  scales_from_exp(E, s_in, s_out);
+  scales_from_exp(E, ns, s_in, s_out);
   if (tid == 0) rs[row] = live ? s_out : 0.0;
   const int Kp = nkb * KB;
+  const long long dstride = (long long)nkb * rows_pad * KB;
   for (int k8 = tid * 8; k8 < Kp; k8 += 256 * 8) {
-    double t[8];
+    unsigned long long z[2][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = (live && k8 + i < Kc) ? (x[k8 + i] * s_in) * kFirstDigit : 0.0;
+    for (int i = 0; i < 8; ++i) z[i >> 2][i & 3] = digits_of((live && k8 + i < Kc) ? x[k8 + i] : 0.0, s_in, ns);
     const int kb = k8 >> 6;
     int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & 63);
     for (int s = 0; s < ns; ++s) {
-      uint32_t lo = 0, hi = 0;
+      const int p = ns - 1 - s;   // digit s has weight 256^(ns - 1 - s)
+      *reinterpret_cast<uint2*>(dst + s * dstride) = make_uint2(gather_byte(z[0], p), gather_byte(z[1], p));
+    }
+  }
+}
+
+// Same, with the row cached in shared memory between the maximum pass and the digit pass (one DRAM read instead of two:
+// with 8 rows per SM in flight the rows of one wave exceed L2 and the plain kernel re-reads them from DRAM).
+// 1024 threads, one CTA per SM (Kp doubles of dynamic shared memory).
+__global__ void __launch_bounds__(1024, 1) split_rows_smem_kernel(const double* __restrict__ X, long long ld, int rows,
+                                                                  int Kc, int rows_pad, int nkb, int ns,
+                                                                  int8_t* __restrict__ out, double* __restrict__ rs) {
+  extern __shared__ __align__(16) double rowbuf[];
+  __shared__ uint32_t redE[32];
+  const int tid = threadIdx.x;
+  const int Kp = nkb * KB;
+  const long long dstride = (long long)nkb * rows_pad * KB;
+  const bool vec = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  for (int row = blockIdx.x; row < rows_pad; row += gridDim.x) {
+    const bool live = row < rows;
+    const double* x = X + (long long)row * ld;
+    uint32_t E = 0;
+    __syncthreads();   // previous row's digit pass is done with rowbuf / redE
+    if (live) {
+      if (vec) {
+        const int K2 = Kc >> 1;
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        double2* r2 = reinterpret_cast<double2*>(rowbuf);
+        for (int k = tid; k < K2; k += 4096) {   // four 16-byte loads per thread in flight
+          double2 v[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const double qd = rint(t[i]);
-        t[i] = (t[i] - qd) * kDigitBase;
-        const uint32_t b = (uint32_t)((int)qd) & 0xFFu;
-        if (i < 4) lo |= b << (8 * i); else hi |= b << (8 * (i - 4));
+          for (int u = 0; u < 4; ++u) v[u] = (k + 1024 * u < K2) ? x2[k + 1024 * u] : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (k + 1024 * u < K2) r2[k + 1024 * u] = v[u];
+            E = max(E, max(((uint32_t)(__double_as_longlong(v[u].x) >> 52)) & 0x7FFu,
+                           ((uint32_t)(__double_as_longlong(v[u].y) >> 52)) & 0x7FFu));
+          }
+        }
+        if ((Kc & 1) && tid == 0) {
+          rowbuf[Kc - 1] = x[Kc - 1];
+          E = max(E, ((uint32_t)(__double_as_longlong(x[Kc - 1]) >> 52)) & 0x7FFu);
+        }
+      } else {
+        for (int k = tid; k < Kc; k += 1024) {
+          const double v = x[k];
+          rowbuf[k] = v;
+          E = max(E, ((uint32_t)(__double_as_longlong(v) >> 52)) & 0x7FFu);
+        }
       }
-      *reinterpret_cast<uint2*>(dst + (long long)s * nkb * rows_pad * KB) = make_uint2(lo, hi);
+    }
+    for (int k = Kc + tid; k < Kp; k += 1024) rowbuf[k] = 0.0;   // K padding of the last block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const uint32_t t = __shfl_xor_sync(0xffffffffu, E, o); E = t > E ? t : E; }
+    if ((tid & 31) == 0) redE[tid >> 5] = E;
+    __syncthreads();
+    E = redE[0];
+#pragma unroll
+    for (int w = 1; w < 32; ++w) E = redE[w] > E ? redE[w] : E;
+    double s_in, s_out;
+    scales_from_exp(E, ns, s_in, s_out);
+    if (tid == 0) rs[row] = live ? s_out : 0.0;
+    for (int k8 = tid * 8; k8 < Kp; k8 += 1024 * 8) {
+      unsigned long long z[2][4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const double2 v = live ? *reinterpret_cast<const double2*>(rowbuf + k8 + i) : make_double2(0.0, 0.0);
+        z[i >> 2][i & 3] = digits_of(v.x, s_in, ns);
+        z[i >> 2][(i & 3) + 1] = digits_of(v.y, s_in, ns);
+      }
+      const int kb = k8 >> 6;
+      int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & 63);
+      for (int s = 0; s < ns; ++s) {
+        const int p = ns - 1 - s;
+        *reinterpret_cast<uint2*>(dst + s * dstride) = make_uint2(gather_byte(z[0], p), gather_byte(z[1], p));
+      }
     }
   }
 }
@@ -499,6 +612,7 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
   if (j >= cols) return;
   const int k0 = blockIdx.y * 64, k1 = min(Kc, k0 + 64);
   uint32_t E = 0;
+#pragma unroll 8
   for (int k = k0; k < k1; ++k) {
     const uint32_t e = ((uint32_t)(__double_as_longlong(X[(long long)k * ld + j]) >> 52)) & 0x7FFu;
     E = e > E ? e : E;
@@ -515,25 +629,25 @@ __global__ void __launch_bounds__(256) split_cols_kernel(const double* __restric
   const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
   const int j = blockIdx.x * 64 + tx, kb = blockIdx.y;
   double s_in = 0.0, s_out = 0.0;
-  if (j < cols) scales_from_exp(Ein[j], s_in, s_out);
+  if (j < cols) scales_from_exp(Ein[j], ns, s_in, s_out);
   if (kb == 0 && ty == 0) rs[j] = s_out;
-  for (int g = ty; g < 16; g += 4) {   // group of 4 consecutive contraction steps
-    double t[4];
+  double xv[4][4];
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {   // all 16 loads of the thread in flight
+    const int g = ty + 4 * gi;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = kb * 64 + 4 * g + i;
-      t[i] = (j < cols && k < Kc) ? (X[(long long)k * ld + j] * s_in) * kFirstDigit : 0.0;
+      xv[gi][i] = (j < cols && k < Kc) ? X[(long long)k * ld + j] : 0.0;
     }
-    for (int s = 0; s < ns; ++s) {
-      uint32_t w = 0;
+  }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const double qd = rint(t[i]);
-        t[i] = (t[i] - qd) * kDigitBase;
-        w |= ((uint32_t)((int)qd) & 0xFFu) << (8 * i);
-      }
-      tile[s][tx][g] = w;
-    }
+  for (int gi = 0; gi < 4; ++gi) {   // group of 4 consecutive contraction steps -> one word per digit
+    const int g = ty + 4 * gi;
+    unsigned long long z[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = digits_of(xv[gi][i], s_in, ns);
+    for (int s = 0; s < ns; ++s) tile[s][tx][g] = gather_byte(z, ns - 1 - s);
   }
   __syncthreads();
   // write: per digit and column one 64-byte row = 4 x 16 bytes
@@ -604,7 +718,18 @@ static int sm_count() {
 static int split_operand(const double* X, long long ld, int kmajor, int rows, int Kc, int rows_pad, int nkb, int ns,
                          int8_t* out, double* rs, uint32_t* Etmp, cudaStream_t stream) {
   if (kmajor) {
-    split_rows_kernel<<<rows_pad, 256, 0, stream>>>(X, ld, rows, Kc, rows_pad, nkb, ns, out, rs);
+    const size_t smem = (size_t)nkb * KB * sizeof(double);
+    if (smem <= 200 * 1024 && rows_pad >= 2 * sm_count()) {   // long operand: cache each row in shared memory
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(split_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+      }
+      split_rows_smem_kernel<<<sm_count(), 1024, smem, stream>>>(X, ld, rows, Kc, rows_pad, nkb, ns, out, rs);
+    } else {
+      split_rows_kernel<<<rows_pad, 256, 0, stream>>>(X, ld, rows, Kc, rows_pad, nkb, ns, out, rs);
+    }
     FCEST_CHECK_LAUNCH();
   } else {
     cudaError_t e = cudaMemsetAsync(Etmp, 0, (size_t)rows_pad * 4, stream);

@@ -35,10 +35,10 @@ _side_streams: dict = {}
 OVERLAP_BACKWARD = True
 
 
-def _side_stream(dev) -> torch.cuda.Stream:
-    """One auxiliary stream per device: the latency-bound single-matrix chain (kernel matrix ->
-    Cholesky -> inverse -> P) runs on it underneath the throughput kernels of the main stream."""
-    key = str(dev)
+def _side_stream(dev, index: int = 0) -> torch.cuda.Stream:
+    """Auxiliary streams per device.  0: the latency-bound single-matrix chain (kernel matrix -> Cholesky -> inverse -> P)
+    and the d q_sqrt chain of the backward pass; 1: the Monte-Carlo draw of an evaluation."""
+    key = (str(dev), index)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=dev)
     return _side_streams[key]

@@ -145,7 +145,18 @@ class _WishartProcessBase:
         """
         x, y = self._data(data)
         lik = self.likelihood
-        fmean, fvar, kl, st = self._moments(x)
+        if epsilon is None:
+            # the Monte-Carlo draw does not depend on the conditional: generate it on its own stream underneath it
+            main = torch.cuda.current_stream(self.device)
+            rng_stream = cond._side_stream(self.device, 1)
+            rng_stream.wait_stream(main)
+            with torch.cuda.stream(rng_stream):
+                epsilon = lik._draw((lik.num_mc_samples, y.shape[0], self.D * self.nu))
+            fmean, fvar, kl, st = self._moments(x)
+            main.wait_stream(rng_stream)
+            epsilon.record_stream(main)
+        else:
+            fmean, fvar, kl, st = self._moments(x)
         out = lik.variational_expectations(x, fmean, fvar, y, epsilon=epsilon, need_grad=True)
         elbo = torch.empty(1, dtype=F64, device=self.device)
         ops.sum_into(out["ve"], out["ve"].numel(), 1, 1.0, elbo, False)

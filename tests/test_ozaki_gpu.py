@@ -1,6 +1,6 @@
 """fcest_dgemm_ozaki (fp64 GEMM emulated on the int8 tensor cores: tcgen05.mma kind::i8, TMEM, TMA) against torch's
-float64 matmul.  The error model of the scheme (ozaki.cu header): with ns base-254 digits per operand row,
-|C - C_ref|[i][j] <= (ns + 2) K 254^(-ns) (2 max|A_i|) (2 max|B_j|)  (+ fp64 rounding of the reference itself)."""
+float64 matmul.  The error model of the scheme (ozaki.cu header): with ns base-256 digits per operand row,
+|C - C_ref|[i][j] <= 4 (ns + 2) K 256^(-ns) (2 max|A_i|) (2 max|B_j|)  (+ fp64 rounding of the reference itself)."""
 import numpy as np
 import pytest
 import torch
@@ -37,7 +37,7 @@ def _check(C, A, B, slices, alpha=1.0, bias=None):
     ref = alpha * (A @ B.t())
     if bias is not None:
         ref = ref + bias[:, None]
-    bound = (slices + 2) * K * 254.0 ** (-slices) * (2 * A.abs().amax(1))[:, None] * (2 * B.abs().amax(1))[None, :]
+    bound = 4 * (slices + 2) * K * 256.0 ** (-slices) * (2 * A.abs().amax(1))[:, None] * (2 * B.abs().amax(1))[None, :]
     bound = abs(alpha) * bound + 1e-15 * K ** 0.5 * (A.abs().amax(1)[:, None] * B.abs().amax(1)[None, :]) * abs(alpha) + 1e-300
     bound = bound + 4e-16 * ref.abs()   # rounding of the bias addition / the final scaling
     err = (C - ref).abs()
