@@ -41,12 +41,16 @@ namespace fcest {
 namespace oz {
 
 constexpr int TM = 128, TN = 128;       // output tile
-constexpr int KB = 64;                   // bytes (= int8 elements) of K per staged block
-constexpr int TILE_BYTES = TM * KB;      // 8 KB per digit tile
+#ifndef FCEST_OZAKI_KB
+#define FCEST_OZAKI_KB 64
+#endif
+constexpr int KB = FCEST_OZAKI_KB;       // bytes (= int8 elements) of K per staged block: 32 (one MMA K step) or 64
+constexpr int TILE_BYTES = TM * KB;      // 4 / 8 KB per digit tile
+static_assert(KB == 32 || KB == 64, "K block");
 constexpr int MAX_NS = 7;                // digits per operand (all digit tiles of two K blocks must fit shared memory)
 constexpr int NUM_THREADS = 320;         // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int SMEM_BAR = 512;
-constexpr int SMEM_TOTAL = 28 * TILE_BYTES + SMEM_BAR + 1024;  // 28 tile slots + barriers + alignment slack
+constexpr int SMEM_TOTAL = 224 * 1024 + SMEM_BAR + 1024;       // tile slots + barriers + alignment slack
 
 struct Params {
   int M, N, tiles_m, tiles_n, nkb, ksplit, ns;
@@ -103,7 +107,10 @@ __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, u
 // position of byte b (0..63) of row r inside a 128-row x 64-byte tile in the 64-byte swizzle the MMA descriptor names:
 // the 16-byte chunk index is XORed with bits 1-2 of the row.  The digit arrays are stored pre-swizzled, so a tile is a
 // plain contiguous copy.
-__host__ __device__ __forceinline__ int swz64(int r, int b) { return r * KB + ((((b >> 4) ^ (r >> 1)) & 3) << 4) + (b & 15); }
+__host__ __device__ __forceinline__ int swz64(int r, int b) {
+  if (KB == 64) return r * 64 + ((((b >> 4) ^ (r >> 1)) & 3) << 4) + (b & 15);   // 64-byte swizzle: chunk ^= row bits 1-2
+  return r * 32 + ((((b >> 4) ^ (r >> 2)) & 1) << 4) + (b & 15);                 // 32-byte swizzle: chunk ^= row bit 2
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -173,15 +180,17 @@ __device__ __forceinline__ bool elect_one() {
 // Operand staging: NSLOT tile slots of 8 KB handed out FIFO in stages of 2 nsl slots (all A digits, then all B digits
 // of one K block); stage i signals full[i % NBAR] / empty[i % NBAR].  Both the producer and the MMA warp derive the
 // slot positions from the same deterministic sequence.
-constexpr int NSLOT = 28;
-constexpr int NBAR = 8;
+constexpr int NSLOT = 224 * 1024 / TILE_BYTES;   // 28 slots of 8 KB or 56 of 4 KB
+constexpr int NBAR = 16;
+constexpr int NBAR_LOG = 4;
 static_assert(NSLOT * TILE_BYTES + SMEM_BAR + 1024 <= 232448, "shared memory budget");
 
 template <int NS, int P>
 __device__ __forceinline__ void mma_stage(uint32_t lo0, uint32_t pos, uint32_t tmem_base, uint32_t first_kb) {
   using S = Sched<NS>;
   constexpr int nsl = S::nsl(P), d_hi = S::d_hi(P), d_lo = S::d_lo(P);
-  constexpr uint64_t hi = ((uint64_t)(512 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)4 << 29)) << 32;  // SBO, version, SW64
+  // SBO = 8 rows, descriptor version 1, layout 4 = SWIZZLE_64B / 6 = SWIZZLE_32B
+  constexpr uint64_t hi = ((uint64_t)((8 * KB) >> 4) | ((uint64_t)1 << 14) | ((uint64_t)(KB == 64 ? 4 : 6) << 29)) << 32;
   uint32_t b_lo[nsl];
 #pragma unroll
   for (int t = 0; t < nsl; ++t) {
@@ -200,7 +209,7 @@ __device__ __forceinline__ void mma_stage(uint32_t lo0, uint32_t pos, uint32_t t
       const uint32_t acc = tmem_base + (uint32_t)((d_hi - (s + t)) * TN);
       const uint32_t keep = s > 0 ? 1u : (first_kb ? 0u : 1u);   // (0, d) is the first product of order d in a unit
       umma_i8(acc, hi | a_lo, hi | b_lo[t], kInstrDesc, keep);
-      umma_i8(acc, hi | (a_lo + 2), hi | (b_lo[t] + 2), kInstrDesc, 1u);   // second K = 32 step: +32 bytes
+      if (KB == 64) umma_i8(acc, hi | (a_lo + 2), hi | (b_lo[t] + 2), kInstrDesc, 1u);   // second K = 32 step: +32 bytes
     }
   }
 }
@@ -213,6 +222,7 @@ ozaki_gemm_kernel(const Params p) {
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + NSLOT * TILE_BYTES;
   const uint32_t full = bars, empty = bars + 8 * NBAR, tfull = empty + 8 * NBAR, tempty = tfull + 32, tptr = tempty + 32;
+  static_assert(16 * NBAR + 64 + 8 <= SMEM_BAR, "barrier area");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = p.tiles_m * p.tiles_n;
   const int units = tiles * p.ksplit;
@@ -235,7 +245,8 @@ ozaki_gemm_kernel(const Params p) {
 
   if (warp == 0) {
     // ===================================== TMA producer (warp-uniform loop, one elected lane issues) ==========
-    uint32_t seq = 0, tail = 0, pos = 0, free_slots = NSLOT, sizes = 0;   // sizes: 4 bits per in-flight stage
+    uint32_t seq = 0, tail = 0, pos = 0, free_slots = NSLOT;
+    unsigned long long sizes = 0;   // 4 bits per in-flight stage (stage sizes <= 14 slots)
     long long w_e = 0;
     const long long t_begin = dbg ? clock64() : 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -248,12 +259,12 @@ ozaki_gemm_kernel(const Params p) {
         const uint32_t n = 2u * nsl;
         for (int kb = kb0; kb < kb1; ++kb) {
           while (free_slots < n || seq - tail >= (uint32_t)NBAR) {   // reclaim the oldest stage once the MMAs are done
-            mbar_wait_t(empty + 8 * (tail & (NBAR - 1)), (tail >> 3) & 1u, w_e, dbg);
-            free_slots += (sizes >> (4 * (tail & (NBAR - 1)))) & 15u;
+            mbar_wait_t(empty + 8 * (tail & (NBAR - 1)), (tail >> NBAR_LOG) & 1u, w_e, dbg);
+            free_slots += (uint32_t)((sizes >> (4 * (tail & (NBAR - 1)))) & 15ull);
             ++tail;
           }
           const uint32_t sh = 4 * (seq & (NBAR - 1));
-          sizes = (sizes & ~(15u << sh)) | (n << sh);
+          sizes = (sizes & ~(15ull << sh)) | ((unsigned long long)n << sh);
           free_slots -= n;
           if (elect_one()) {
             const uint32_t fb = full + 8 * (seq & (NBAR - 1));
@@ -304,7 +315,7 @@ ozaki_gemm_kernel(const Params p) {
         if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> 3) & 1u, w_f, dbg);
+          mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> NBAR_LOG) & 1u, w_f, dbg);
           tc_fence_after();
           if (elect_one()) {
             if (ps == 0) mma_stage<NS, 0>(lo0, pos, tmem_base, kb == kb0);
@@ -453,7 +464,8 @@ __global__ void __launch_bounds__(256) ozaki_fixup_kernel(const Params p) {
 // biased exponent field E of max|x| -> (input scale 2^(8 ns - 2 - e), output scale 2^(e - 6)), e = E - 1022; zero / tiny
 // rows -> 0.
 __device__ __forceinline__ void scales_from_exp(uint32_t E, int ns, double& s_in, double& s_out) {
-  if (E < 64u || E > 1980u) { s_in = 0.0; s_out = 0.0; return; }
+  if (E < 64u) { s_in = 0.0; s_out = 0.0; return; }                         // |row| < 2^-958: zero
+  if (E > 1980u) { s_in = 0.0; s_out = __longlong_as_double(0x7FF8000000000000LL); return; }   // Inf / NaN / > 2^958: NaN row
   s_in = __longlong_as_double((long long)(2043u + 8u * (uint32_t)ns - E) << 52);
   s_out = __longlong_as_double((long long)(E - 5u) << 52);
 }
@@ -522,8 +534,8 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const double* __restric
     unsigned long long z[2][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) z[i >> 2][i & 3] = digits_of((live && k8 + i < Kc) ? x[k8 + i] : 0.0, s_in, ns);
-    const int kb = k8 >> 6;
-    int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & 63);
+    const int kb = k8 / KB;
+    int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & (KB - 1));
     for (int s = 0; s < ns; ++s) {
       const int p = ns - 1 - s;   // digit s has weight 256^(ns - 1 - s)
       *reinterpret_cast<uint2*>(dst + s * dstride) = make_uint2(gather_byte(z[0], p), gather_byte(z[1], p));
@@ -595,8 +607,8 @@ __global__ void __launch_bounds__(1024, 1) split_rows_smem_kernel(const double* 
         z[i >> 2][i & 3] = digits_of(v.x, s_in, ns);
         z[i >> 2][(i & 3) + 1] = digits_of(v.y, s_in, ns);
       }
-      const int kb = k8 >> 6;
-      int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & 63);
+      const int kb = k8 / KB;
+      int8_t* dst = out + ((long long)kb * rows_pad + (row & ~127)) * KB + swz64(row & 127, k8 & (KB - 1));
       for (int s = 0; s < ns; ++s) {
         const int p = ns - 1 - s;
         *reinterpret_cast<uint2*>(dst + s * dstride) = make_uint2(gather_byte(z[0], p), gather_byte(z[1], p));
@@ -656,7 +668,9 @@ __global__ void __launch_bounds__(256) split_cols_kernel(const double* __restric
     const uint32_t* src = &tile[s][col][part * 4];
     const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
     const int orow = blockIdx.x * 64 + col;
-    int8_t* dst = out + (((long long)s * nkb + kb) * cols_pad + (orow & ~127)) * KB + swz64(orow & 127, part * 16);
+    const int kglob = kb * 64 + part * 16, kbK = kglob / KB;   // this block covers 64 contraction steps = 64 / KB K blocks
+    if (kbK >= nkb) continue;
+    int8_t* dst = out + (((long long)s * nkb + kbK) * cols_pad + (orow & ~127)) * KB + swz64(orow & 127, kglob & (KB - 1));
     *reinterpret_cast<uint4*>(dst) = v;
   }
 }
@@ -681,12 +695,12 @@ static Plan make_plan(int M, int N, int K, int ns, int sms) {
   pl.tiles_n = pl.Np / TN;
   pl.nkb = (int)((K + KB - 1) / KB);
   const int tiles = pl.tiles_m * pl.tiles_n;
-  // K split: fewest splits within 3 % of the best wave efficiency; every unit keeps >= 8 K blocks and at most 256
+  // K split: fewest splits within 3 % of the best wave efficiency; every unit keeps >= 512 and at most 16384 contraction steps
   // (int32 accumulators: 7 pairs x 16384 terms x 127^2 < 2^31)
-  int ks_min = (pl.nkb + 255) / 256, best = ks_min;
+  int ks_min = (pl.nkb * KB + 16383) / 16384, best = ks_min;
   double best_cost = 1e300;
   for (int ks = ks_min; ks <= 16; ++ks) {
-    if (ks > ks_min && pl.nkb / ks < 8) break;
+    if (ks > ks_min && pl.nkb * KB / 64 / ks < 8) break;
     const double cost = (double)((tiles * (long long)ks + sms - 1) / sms) / ks;
     if (cost < best_cost * 0.97) { best_cost = cost; best = ks; }
   }
@@ -736,7 +750,7 @@ static int split_operand(const double* X, long long ld, int kmajor, int rows, in
     if (e != cudaSuccess) return (int)e;
     colmax_kernel<<<dim3((rows + 255) / 256, (Kc + 63) / 64), 256, 0, stream>>>(X, ld, Kc, rows, Etmp);
     FCEST_CHECK_LAUNCH();
-    split_cols_kernel<<<dim3(rows_pad / 64, nkb), 256, 0, stream>>>(X, ld, Kc, rows, rows_pad, nkb, ns, Etmp, out, rs);
+    split_cols_kernel<<<dim3(rows_pad / 64, (nkb * KB + 63) / 64), 256, 0, stream>>>(X, ld, Kc, rows, rows_pad, nkb, ns, Etmp, out, rs);
     FCEST_CHECK_LAUNCH();
   }
   return 0;

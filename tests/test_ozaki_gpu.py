@@ -108,3 +108,18 @@ def test_ozaki_projection_shapes_match_dmma(cuda):
         ops.dgemm_ozaki(*args, got, slices=6, **kw)
         rel = float((got - ref).abs().max() / ref.abs().max())
         assert rel < 1e-10, (args[:5], rel)
+
+
+def test_ozaki_non_finite_operands_give_nan_rows(cuda):
+    """A NaN / Inf anywhere in an operand row poisons the matching output row or column (as a native GEMM would), it is
+    not silently treated as zero."""
+    A, B = _operands(140, 130, 300, True, True, seed=2)
+    A[3, 17] = float("nan")
+    B[5, 0] = float("inf")
+    C = _run(A, B, True, False, 6)
+    assert torch.isnan(C[3]).all() and torch.isnan(C[:, 5]).all()
+    keep = torch.ones(140, dtype=torch.bool); keep[3] = False
+    keepc = torch.ones(130, dtype=torch.bool); keepc[5] = False
+    ref = A[keep] @ B[keepc].t()
+    assert torch.isfinite(C[keep][:, keepc]).all()
+    assert float((C[keep][:, keepc] - ref).abs().max() / ref.abs().max()) < 1e-10
