@@ -48,7 +48,7 @@ constexpr int KB = FCEST_OZAKI_KB;       // bytes (= int8 elements) of K per sta
 constexpr int TILE_BYTES = TM * KB;      // 4 / 8 KB per digit tile
 static_assert(KB == 32 || KB == 64, "K block");
 constexpr int MAX_NS = 7;                // digits per operand (all digit tiles of two K blocks must fit shared memory)
-constexpr int NUM_THREADS = 320;         // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int NUM_THREADS = 352;         // warp 0 producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
 constexpr int SMEM_BAR = 512;
 constexpr int SMEM_TOTAL = 224 * 1024 + SMEM_BAR + 1024;       // tile slots + barriers + alignment slack
 
@@ -294,8 +294,13 @@ ozaki_gemm_kernel(const Params p) {
       p.dbg[8 * blockIdx.x + 0] = clock64() - t_begin;
       p.dbg[8 * blockIdx.x + 1] = w_e;
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer (warp-uniform loop, one elected lane issues) ============
+  } else if (warp == 1 || warp == 10) {
+    // ===================================== MMA issuers: two warps take alternate stages =====================
+    // One stage boundary (test the next full barrier, rebuild descriptors, commit) costs ~200 cycles in which the MMA
+    // queue of a single issuer drains.  With two issuers the idle one has done all of that for stage i + 1 while the
+    // other issues stage i; the hand-over is a named barrier (bar.arrive / bar.sync, 64 threads), so the tensor pipe
+    // sees one uninterrupted stream.  Issue order = stage order, which keeps "first product overwrites" correct.
+    const uint32_t me = warp == 1 ? 0u : 1u;
     uint32_t seq = 0, pos = 0;
     uint32_t use0 = 0, use1 = 0, use2 = 0, use3 = 0;   // how often each accumulator has been handed to the epilogue
     long long w_f = 0, w_te = 0;
@@ -308,39 +313,44 @@ ozaki_gemm_kernel(const Params p) {
       for (int ps = 0; ps < S::NPASS; ++ps) {
         const int nbuf = S::d_hi(ps) - S::d_lo(ps) + 1;
         const uint32_t n = 2u * S::nsl(ps);
-        // accumulators of this pass must have been drained by the epilogue
-        if (nbuf > 0) mbar_wait_t(tempty + 0, (use0 & 1u) ^ 1u, w_te, dbg);
-        if (nbuf > 1) mbar_wait_t(tempty + 8, (use1 & 1u) ^ 1u, w_te, dbg);
-        if (nbuf > 2) mbar_wait_t(tempty + 16, (use2 & 1u) ^ 1u, w_te, dbg);
-        if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
-        tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> NBAR_LOG) & 1u, w_f, dbg);
-          tc_fence_after();
-          if (elect_one()) {
-            if (ps == 0) mma_stage<NS, 0>(lo0, pos, tmem_base, kb == kb0);
-            else mma_stage<NS, (S::NPASS > 1 ? 1 : 0)>(lo0, pos, tmem_base, kb == kb0);
-            tc_commit(empty + 8 * (seq & (NBAR - 1)));
+          if ((seq & 1u) == me) {
+            if (kb == kb0) {   // first stage of the pass: its accumulators must have been drained by the epilogue
+              if (nbuf > 0) mbar_wait_t(tempty + 0, (use0 & 1u) ^ 1u, w_te, dbg);
+              if (nbuf > 1) mbar_wait_t(tempty + 8, (use1 & 1u) ^ 1u, w_te, dbg);
+              if (nbuf > 2) mbar_wait_t(tempty + 16, (use2 & 1u) ^ 1u, w_te, dbg);
+              if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
+            }
+            mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> NBAR_LOG) & 1u, w_f, dbg);
+            if (seq > 0) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");   // stage seq - 1 has been issued
+            tc_fence_after();
+            if (elect_one()) {
+              if (ps == 0) mma_stage<NS, 0>(lo0, pos, tmem_base, kb == kb0);
+              else mma_stage<NS, (S::NPASS > 1 ? 1 : 0)>(lo0, pos, tmem_base, kb == kb0);
+              tc_commit(empty + 8 * (seq & (NBAR - 1)));
+              if (kb + 1 == kb1) {   // last stage of the pass: publish the accumulators
+                if (nbuf > 0) tc_commit(tfull + 0);
+                if (nbuf > 1) tc_commit(tfull + 8);
+                if (nbuf > 2) tc_commit(tfull + 16);
+                if (nbuf > 3) tc_commit(tfull + 24);
+              }
+            }
+            __syncwarp();
+            asm volatile("bar.arrive %0, 64;" ::"r"(1u + (seq & 1u)) : "memory");   // hand over to the issuer of stage seq + 1
           }
-          __syncwarp();
           pos += n;
           pos = pos >= NSLOT ? pos - NSLOT : pos;
           ++seq;
         }
-        if (elect_one()) {
-          if (nbuf > 0) tc_commit(tfull + 0);
-          if (nbuf > 1) tc_commit(tfull + 8);
-          if (nbuf > 2) tc_commit(tfull + 16);
-          if (nbuf > 3) tc_commit(tfull + 24);
-        }
-        __syncwarp();
         if (nbuf > 0) ++use0;
         if (nbuf > 1) ++use1;
         if (nbuf > 2) ++use2;
         if (nbuf > 3) ++use3;
       }
     }
-    if (dbg && lane == 0) {
+    // the last hand-over has no taker: consume it so that the named barrier is idle when the kernel ends
+    if (seq > 0 && ((seq - 1u) & 1u) != me) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");
+    if (dbg && lane == 0 && me == 0) {
       p.dbg[8 * blockIdx.x + 3] = clock64() - t_begin;
       p.dbg[8 * blockIdx.x + 4] = w_f;
       p.dbg[8 * blockIdx.x + 6] = w_te;
