@@ -27,6 +27,10 @@ struct LikParams {
 int launch_loglik_warp(const LikParams& p, cudaStream_t stream, int* part_rows);
 bool loglik_warp_supported(int D, int nu);
 
+// Sub-warp variant (likelihood_subwarp.cu), D <= 7: one 8-lane group per time step, registers + shuffles only.
+int launch_loglik_subwarp(const LikParams& p, cudaStream_t stream, int* part_rows);
+bool loglik_subwarp_supported(int D, int nu);
+
 // Shared-memory-tiled CTA-per-matrix variant (likelihood_tiles.cu), 8 <= D <= 207.  p.ws must point to
 // loglik_tiles_scratch_bytes(D, nu) bytes of global scratch.  Same return convention as above.
 int launch_loglik_tiles(LikParams p, cudaStream_t stream, int* part_rows);

@@ -325,9 +325,16 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   // D <= 55: warp-per-matrix kernel (likelihood_warp.cu); FCEST_LIK_IMPL=cta forces the older CTA-per-time-step
   // kernels of this file (shared memory for D <= ~80, L2 scratch above)
   static const bool force_cta = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cta"); }();
+  static const bool force_warp = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "warp"); }();
   bool launched = false;
   int part_rows = N;  // rows of the A_bar / lam_bar partial workspaces that the kernel filled
-  if (!force_cta && loglik_warp_supported(D, nu)) {
+  // D <= 7: sub-warp kernel (likelihood_subwarp.cu): four problems per warp, registers and shuffles only
+  if (!force_cta && !force_warp && loglik_subwarp_supported(D, nu)) {
+    const int rc = launch_loglik_subwarp(p, stream, &part_rows);
+    if (rc > 0) return rc;
+    launched = (rc == 0);
+  }
+  if (!launched && !force_cta && loglik_warp_supported(D, nu)) {
     const int rc = launch_loglik_warp(p, stream, &part_rows);
     if (rc > 0) return rc;
     launched = (rc == 0);

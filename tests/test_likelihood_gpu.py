@@ -196,3 +196,36 @@ def test_kernels_are_run_to_run_deterministic(cuda):
     first = sw.overlapping_windowed_cov_estimation(30)
     for _ in range(4):
         assert np.array_equal(sw.overlapping_windowed_cov_estimation(30), first)
+
+
+@pytest.mark.parametrize("D,S,vector_a", [(1, 1, False), (2, 5, False), (3, 5, False), (4, 3, True), (5, 2, False), (6, 9, False), (7, 4, True)])
+def test_loglik_subwarp_kernel(cuda, D, S, vector_a):
+    """D <= 7: four problems per warp (8-lane groups, registers + shuffles, likelihood_subwarp.cu); also more time steps
+    than one block of groups and a sample count that is not a multiple of anything."""
+    _check(N=37, D=D, S=S, seed=300 + D, vector_a=vector_a)
+
+
+def test_loglik_subwarp_bad_pivot_and_forced_warp_kernel_agree(cuda):
+    from fcest_b200 import ops
+    N, D, S = 5, 3, 2
+    fmean, fvar, y, A, lam, eps = _inputs(N, D, S, 5)
+    lam0 = torch.full((D,), -800.0, dtype=torch.float64)
+    out = ops.wishart_loglik(ops.as_pitched(torch.zeros_like(fmean).cuda()), ops.as_pitched(fvar.cuda()),
+                             torch.zeros_like(eps).cuda(), y.cuda(), A.cuda(), lam0.cuda(), need_grad=False)
+    assert (out["info"].cpu().numpy() == 1).all() and torch.isnan(out["ve"]).all()
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "from fcest_b200 import ops\n"
+        "import importlib.util as iu; sp = iu.spec_from_file_location('tl', %r); tl = iu.module_from_spec(sp); sp.loader.exec_module(tl)\n"
+        "fm, fv, y, A, lam, eps = tl._inputs(21, 6, 4, 12)\n"
+        "o = ops.wishart_loglik(ops.as_pitched(fm.cuda()), ops.as_pitched(fv.cuda()), eps.cuda(), y.cuda(), A.cuda(), lam.cuda())\n"
+        "np.savez(sys.argv[1], **{k: v.cpu().numpy() for k, v in o.items()})\n" % (ROOT, os.path.abspath(__file__)))
+    outs = []
+    for impl in ("subwarp", "warp"):
+        path = os.path.join(ROOT, "gpurun_out", f"_lik_small_{impl}.npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, FCEST_LIK_IMPL=impl), cwd=ROOT)
+        outs.append(np.load(path))
+    for k in ("ve", "g_fmean", "g_fvar", "gA", "glam"):
+        a, b = outs[0][k], outs[1][k]
+        assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-300), k
