@@ -7,9 +7,10 @@
 // A D x D problem with D <= 7 and its bordered row (row D = y^T, so that z = L^-1 y falls out of the factorisation)
 // is at most 8 x 8: lane i of the group owns row i of G (nu <= 8 values), of Sigma / L and of every right-hand side.
 // The warp-per-matrix kernel pads such a problem to one 8 x 8 DMMA tile on 32 lanes; here four problems share a warp
-// and no tensor-core instruction, shared memory or block barrier is involved.  The group walks the S samples of its
-// time step in order, so the sums over samples (mu_bar, v_bar, A_bar, lam_bar) stay in registers and every output
-// has one owner: deterministic, no atomics.
+// and no tensor-core instruction is involved.  A CTA holds 16 groups: Gs = min(S, 16) groups share a time step (group gs
+// takes the samples s = gs, gs + Gs, ...), 16 / Gs time steps per CTA; the per-group sums over its samples stay in
+// registers and are combined across the groups of a time step through shared memory in group order: every output
+// has one owner and a fixed summation order (deterministic, no atomics).
 #include <math.h>
 
 #include "common.cuh"
@@ -27,13 +28,19 @@ __device__ __forceinline__ double gsum(unsigned mask, double v) {
 }
 
 __global__ void __launch_bounds__(128) wishart_loglik_subwarp_kernel(const LikParams p) {
+  __shared__ double part[16][8][27];        // per group and lane: mu_bar, v_bar, A_bar (8 each), lam_bar, ve, bad
   const int D = p.D, nu = p.nu, R = D * nu, N = p.N;
-  const int n = blockIdx.x * 16 + (threadIdx.x >> 3);
-  if (n >= N) return;                       // whole groups leave together: the shuffle masks name one group only
+  const int Gs = p.S < 16 ? p.S : 16;       // groups per time step
+  const int T = 16 / Gs;                    // time steps per CTA
+  const int grp = threadIdx.x >> 3;
+  const int tl = grp / Gs, gs = grp - tl * Gs;
+  const int n = blockIdx.x * T + tl;
+  const bool active = tl < T && n < N;      // whole groups are active or not: the shuffle masks name one group only
   const int i = threadIdx.x & 7;            // row owned by this lane
   const unsigned mask = 0xFFu << (8 * ((threadIdx.x & 31) >> 3));
   const double wS = 1.0 / p.S;
   const bool row = i < D;
+  if (active) {
 
   // sample-independent pieces of row i: A, fmean, sqrt(fvar), y, softplus(lam)
   double Ar[8], fm[8], sd[8];
@@ -58,7 +65,7 @@ __global__ void __launch_bounds__(128) wishart_loglik_subwarp_kernel(const LikPa
   double lam_bar = 0.0, ve_acc = 0.0;
   int bad = 0;
 
-  for (int s = 0; s < p.S; ++s) {
+  for (int s = gs; s < p.S; s += Gs) {
     const double* ep = p.eps + ((long long)s * N + n) * R;
     double e[8], gk[8], a[8];
 #pragma unroll
@@ -172,7 +179,30 @@ __global__ void __launch_bounds__(128) wishart_loglik_subwarp_kernel(const LikPa
     }
   }
 
-  if (i == 0) {   // every lane saw the same pivots: `bad` agrees across the group
+  // this group's partial sums -> shared memory
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { part[grp][i][c] = mu_bar[c]; part[grp][i][8 + c] = v_bar[c]; part[grp][i][16 + c] = A_bar[c]; }
+  part[grp][i][24] = lam_bar;
+  part[grp][i][25] = ve_acc;
+  part[grp][i][26] = (double)bad;
+  }  // active
+  __syncthreads();
+  if (!active || gs != 0) return;
+  // group 0 of the time step: sum over the groups in order, write the outputs
+  double mu_bar[8], v_bar[8], A_bar[8], lam_bar = 0.0, ve_acc = 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) mu_bar[c] = v_bar[c] = A_bar[c] = 0.0;
+  for (int g2 = 0; g2 < Gs; ++g2) {
+    const double* q = part[grp + g2][i];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { mu_bar[c] += q[c]; v_bar[c] += q[8 + c]; A_bar[c] += q[16 + c]; }
+    lam_bar += q[24];
+    ve_acc += q[25];
+    const int b = (int)q[26];
+    if (b && !bad) bad = b;
+  }
+  if (i == 0) {   // every lane of a group saw the same pivots
     p.ve[n] = bad ? nan("") : ve_acc;
     p.info[n] = bad;
   }
@@ -194,7 +224,8 @@ bool loglik_subwarp_supported(int D, int nu) { return D >= 1 && D <= 7 && nu >= 
 
 int launch_loglik_subwarp(const LikParams& p, cudaStream_t stream, int* part_rows) {
   if (!loglik_subwarp_supported(p.D, p.nu)) return -1;
-  wishart_loglik_subwarp_kernel<<<(p.N + 15) / 16, 128, 0, stream>>>(p);
+  const int Gs = p.S < 16 ? p.S : 16, T = 16 / Gs;
+  wishart_loglik_subwarp_kernel<<<(p.N + T - 1) / T, 128, 0, stream>>>(p);
   *part_rows = p.N;
   return 0;
 }
