@@ -163,6 +163,9 @@ struct Sched {
   __host__ __device__ static constexpr int d_hi(int p) { return p == 0 ? NS - 1 : NS - 5; }
   __host__ __device__ static constexpr int d_lo(int p) { return p == 0 ? (NS > 4 ? NS - 4 : 0) : 0; }
   __host__ __device__ static constexpr int nsl(int p) { return d_hi(p) + 1; }   // digits of each operand the pass needs
+  // K blocks per stage: the short second pass packs several K blocks into one stage (up to 12 tile slots), so that the
+  // fixed cost of a stage boundary is spread over more than a handful of MMAs
+  __host__ __device__ static constexpr int kbs(int p) { return 12 / (2 * nsl(p)) > 1 ? 12 / (2 * nsl(p)) : 1; }
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -256,8 +259,9 @@ ozaki_gemm_kernel(const Params p) {
 #pragma unroll
       for (int ps = 0; ps < S::NPASS; ++ps) {
         const int nsl = S::nsl(ps);
-        const uint32_t n = 2u * nsl;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; kb += S::kbs(ps)) {
+          const int g = kb1 - kb < S::kbs(ps) ? kb1 - kb : S::kbs(ps);   // K blocks in this stage
+          const uint32_t n = 2u * nsl * g;
           while (free_slots < n || seq - tail >= (uint32_t)NBAR) {   // reclaim the oldest stage once the MMAs are done
             mbar_wait_t(empty + 8 * (tail & (NBAR - 1)), (tail >> NBAR_LOG) & 1u, w_e, dbg);
             free_slots += (uint32_t)((sizes >> (4 * (tail & (NBAR - 1)))) & 15ull);
@@ -270,17 +274,20 @@ ozaki_gemm_kernel(const Params p) {
             const uint32_t fb = full + 8 * (seq & (NBAR - 1));
             mbar_expect_tx(fb, n * (uint32_t)TILE_BYTES);
             const long long strideA = (long long)p.nkb * p.tiles_m * TM * KB, strideB = (long long)p.nkb * p.tiles_n * TN * KB;
-            const int8_t* srcA = p.dA + ((long long)kb * p.tiles_m + tm) * TILE_BYTES;
-            const int8_t* srcB = p.dB + ((long long)kb * p.tiles_n + tn) * TILE_BYTES;
-            for (int s = 0; s < nsl; ++s) {
-              uint32_t slot = pos + s;
-              slot = slot >= NSLOT ? slot - NSLOT : slot;
-              bulk_load(base + slot * TILE_BYTES, srcA + s * strideA, TILE_BYTES, fb);
-            }
-            for (int t = 0; t < nsl; ++t) {
-              uint32_t slot = pos + nsl + t;
-              slot = slot >= NSLOT ? slot - NSLOT : slot;
-              bulk_load(base + slot * TILE_BYTES, srcB + t * strideB, TILE_BYTES, fb);
+            for (int j = 0; j < g; ++j) {
+              const int8_t* srcA = p.dA + ((long long)(kb + j) * p.tiles_m + tm) * TILE_BYTES;
+              const int8_t* srcB = p.dB + ((long long)(kb + j) * p.tiles_n + tn) * TILE_BYTES;
+              const uint32_t pj = pos + (uint32_t)(2 * nsl * j);
+              for (int s = 0; s < nsl; ++s) {
+                uint32_t slot = pj + s;
+                slot = slot >= NSLOT ? slot - NSLOT : slot;
+                bulk_load(base + slot * TILE_BYTES, srcA + s * strideA, TILE_BYTES, fb);
+              }
+              for (int t = 0; t < nsl; ++t) {
+                uint32_t slot = pj + nsl + t;
+                slot = slot >= NSLOT ? slot - NSLOT : slot;
+                bulk_load(base + slot * TILE_BYTES, srcB + t * strideB, TILE_BYTES, fb);
+              }
             }
           }
           __syncwarp();
@@ -312,8 +319,9 @@ ozaki_gemm_kernel(const Params p) {
 #pragma unroll
       for (int ps = 0; ps < S::NPASS; ++ps) {
         const int nbuf = S::d_hi(ps) - S::d_lo(ps) + 1;
-        const uint32_t n = 2u * S::nsl(ps);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; kb += S::kbs(ps)) {
+          const int g = kb1 - kb < S::kbs(ps) ? kb1 - kb : S::kbs(ps);   // K blocks in this stage
+          const uint32_t n = 2u * S::nsl(ps) * g;
           if ((seq & 1u) == me) {
             if (kb == kb0) {   // first stage of the pass: its accumulators must have been drained by the epilogue
               if (nbuf > 0) mbar_wait_t(tempty + 0, (use0 & 1u) ^ 1u, w_te, dbg);
@@ -325,10 +333,14 @@ ozaki_gemm_kernel(const Params p) {
             if (seq > 0) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");   // stage seq - 1 has been issued
             tc_fence_after();
             if (elect_one()) {
-              if (ps == 0) mma_stage<NS, 0>(lo0, pos, tmem_base, kb == kb0);
-              else mma_stage<NS, (S::NPASS > 1 ? 1 : 0)>(lo0, pos, tmem_base, kb == kb0);
+              for (int j = 0; j < g; ++j) {
+                uint32_t pj = pos + 2u * S::nsl(ps) * j;
+                pj = pj >= NSLOT ? pj - NSLOT : pj;
+                if (ps == 0) mma_stage<NS, 0>(lo0, pj, tmem_base, kb + j == kb0);
+                else mma_stage<NS, (S::NPASS > 1 ? 1 : 0)>(lo0, pj, tmem_base, kb + j == kb0);
+              }
               tc_commit(empty + 8 * (seq & (NBAR - 1)));
-              if (kb + 1 == kb1) {   // last stage of the pass: publish the accumulators
+              if (kb + g == kb1) {   // last stage of the pass: publish the accumulators
                 if (nbuf > 0) tc_commit(tfull + 0);
                 if (nbuf > 1) tc_commit(tfull + 8);
                 if (nbuf > 2) tc_commit(tfull + 16);
