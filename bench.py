@@ -38,12 +38,14 @@ LIK_KERNEL_NAME = "wishart_loglik_warp_kernel<7> (+ 2 colsum reductions)"
 # capture (a constant from the named profile, NOT measured in the bench run)
 TRAFFIC_BYTES_PER_LAUNCH = 777e6
 TRAFFIC_SOURCE = "constant from profiles/r01_ncu_summary.md (ncu --set full of the round-1 build: 969 / 604 / 758 MB for V, Gk, Tk); not measured in this run"
-# int8-emulated GEMM: DRAM traffic of the GEMM kernel from the ncu --set full capture named below; algorithmic bytes =
-# digit arrays read once (7 x (1280 + 2560) x 20160 B) + the fp64 partial / output tiles written once
-OZAKI_TRAFFIC_BYTES_PER_LAUNCH = 976e6
-OZAKI_TRAFFIC_SOURCE = ("constant from profiles/r02_ncu_ozaki.md (ncu --set full, V = Pk Sk^T: dram read 622 MB + write 354 MB); "
-                        "not measured in this run")
-OZAKI_ALGORITHMIC_BYTES = 7 * (1280 + 2560) * 20160 + 5 * 200 * 128 * 128 * 8
+# int8-emulated GEMM kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of
+# the final build (V: 495 + 361 MB, Gk: 148 + 376 MB, Tk: 297 + 177 MB; profiles/r02_ncu_ozaki.md) -- constants from those
+# captures, NOT measured in the bench run.  Algorithmic bytes = digit arrays read once + the fp64 output (or the split-K
+# partial tiles) written once: V 464 + 131 MB, Gk 139 + 402 MB, Tk 275 + 193 MB.
+OZAKI_TRAFFIC_BYTES_PER_LAUNCH = (856e6 + 524e6 + 474e6) / 3.0
+OZAKI_TRAFFIC_SOURCE = ("constant: mean of the three ncu --set full captures of the final build (V 856 MB, Gk 524 MB, Tk 474 MB per "
+                        "launch; profiles/r02_ncu_ozaki.md); not measured in this run")
+OZAKI_ALGORITHMIC_BYTES = (595e6 + 541e6 + 468e6) / 3.0
 CPU_ARM_BUDGET_S = 200.0   # wall-clock budget of the --impl reference run (full-size evaluations only)
 
 
