@@ -180,6 +180,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Exact int32 -> double without the quarter-rate I2F.F64 conversion: the bits of 2^52 + 2^31 + v are (0x43300000,
+// v ^ 0x80000000), and subtracting 2^52 + 2^31 is exact.  One integer op + one full-rate fp64 add per accumulator entry;
+// the epilogue warps drain 4 x 64 entries per thread and unit, and the next unit's MMAs wait for that drain.
+__device__ __forceinline__ double i32_to_f64(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
 // Operand staging: NSLOT tile slots of 8 KB handed out FIFO in stages of 2 nsl slots (all A digits, then all B digits
 // of one K block); stage i signals full[i % NBAR] / empty[i % NBAR].  Both the producer and the MMA warp derive the
 // slot positions from the same deterministic sequence.
@@ -392,10 +399,10 @@ ozaki_gemm_kernel(const Params p) {
             tmem_ld_wait();
             if (first) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = (double)(int)v[j];
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = i32_to_f64(v[j]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.00390625, (double)(int)v[j]);
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.00390625, i32_to_f64(v[j]));
             }
           }
           tc_fence_before();
