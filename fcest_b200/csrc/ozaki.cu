@@ -31,8 +31,10 @@
 // orders are processed in passes of four (d = ns-1 .. ns-4, then the rest).
 // Work units = (K split, 128 x 128 output tile), dealt round-robin to the CTAs in K-split-major order so that
 // concurrently running CTAs stream the same K range (the digit arrays of one K split stay L2 resident).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "fcest_b200.h"
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 ozaki_gemm_kernel(const Params p) {
   using S = Sched<NS>;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ long long t_done_s;   // diagnostics only: when the previous stage's MMAs had been issued
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + NSLOT * TILE_BYTES;
   const uint32_t full = bars, empty = bars + 8 * NBAR, tfull = empty + 8 * NBAR, tempty = tfull + 32, tptr = tempty + 32;
@@ -317,7 +320,7 @@ ozaki_gemm_kernel(const Params p) {
     const uint32_t me = warp == 1 ? 0u : 1u;
     uint32_t seq = 0, pos = 0;
     uint32_t use0 = 0, use1 = 0, use2 = 0, use3 = 0;   // how often each accumulator has been handed to the epilogue
-    long long w_f = 0, w_te = 0;
+    long long w_f = 0, w_te = 0, w_op = 0, w_busy = 0;
     const long long t_begin = dbg ? clock64() : 0;
     const uint32_t lo0 = ((base & 0x3FFFFu) >> 4) | (1u << 16);
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -337,7 +340,14 @@ ozaki_gemm_kernel(const Params p) {
               if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
             }
             mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> NBAR_LOG) & 1u, w_f, dbg);
+            const long long t_ready = dbg ? clock64() : 0;
             if (seq > 0) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");   // stage seq - 1 has been issued
+            long long t_i0 = 0;
+            if (dbg) {   // operands later than the end of the previous stage's issue = the tensor pipe runs dry
+              const long long td = *reinterpret_cast<volatile long long*>(&t_done_s);
+              if (seq > 0 && t_ready > td) w_op += t_ready - td;
+              t_i0 = clock64();
+            }
             tc_fence_after();
             if (elect_one()) {
               for (int j = 0; j < g; ++j) {
@@ -355,6 +365,11 @@ ozaki_gemm_kernel(const Params p) {
               }
             }
             __syncwarp();
+            if (dbg) {
+              const long long t1 = clock64();
+              w_busy += t1 - t_i0;
+              if (lane == 0) *reinterpret_cast<volatile long long*>(&t_done_s) = t1;
+            }
             asm volatile("bar.arrive %0, 64;" ::"r"(1u + (seq & 1u)) : "memory");   // hand over to the issuer of stage seq + 1
           }
           pos += n;
@@ -369,10 +384,12 @@ ozaki_gemm_kernel(const Params p) {
     }
     // the last hand-over has no taker: consume it so that the named barrier is idle when the kernel ends
     if (seq > 0 && ((seq - 1u) & 1u) != me) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");
-    if (dbg && lane == 0 && me == 0) {
-      p.dbg[8 * blockIdx.x + 3] = clock64() - t_begin;
-      p.dbg[8 * blockIdx.x + 4] = w_f;
-      p.dbg[8 * blockIdx.x + 6] = w_te;
+    if (dbg && lane == 0) {
+      if (me == 0) p.dbg[8 * blockIdx.x + 3] = clock64() - t_begin;
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 2), (unsigned long long)w_busy);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 4), (unsigned long long)w_op);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 6), (unsigned long long)w_te);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 7), (unsigned long long)w_f);
     }
   } else {
     // ===================================== epilogue warps =====================================
@@ -447,6 +464,369 @@ ozaki_gemm_kernel(const Params p) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): two SMs of a TPC share one 256 x 128 output tile
+// ---------------------------------------------------------------------------------------------------------------
+// Why: the single-CTA kernel is bound by L2 -> SM delivery, not by the tensor pipe.  One K block of a 128 x 128 tile
+// needs 2 nsl digit tiles of 8 KB for (pairs) x 2 MMAs of 64 cycles: 47.6 B/clk per SM at 6 digits, 50 B/clk at 5, against
+// the ~42.6 B/clk per SM the L2 delivers with every SM pulling (6300 B/clk chip-wide).  In a CTA pair each SM stages its own
+// 128 rows of A and only HALF of the B tile (64 of the 128 output columns' digit rows); tcgen05.mma.cta_group::2 (M = 256)
+// reads the other half from the peer's shared memory.  Bytes per SM and K block drop by 25 % (35.7 / 37.5 B/clk), shared
+// memory holds three stages instead of 2.3, and the operand read per MMA drops from 8 KB to 6 KB per SM.
+//   * cluster (2, 1, 1); rank 0 (leader) issues every MMA and commit; both CTAs run the same producer schedule, so
+//     digit tiles sit at identical shared-memory offsets in both
+//   * operands arrive through tensor-map TMA with .cta_group::2: the copies of BOTH CTAs complete on the LEADER's full
+//     barrier (the leader expects the bytes of both); the digit arrays are viewed as rows of 2 KB, an A tile is a box of
+//     4 rows, a B half tile a box of 2 rows (the tiles are stored pre-swizzled, so the copy is linear)
+//   * tcgen05.commit ... multicast::cluster releases the stage / publishes the accumulators in both CTAs
+//   * each CTA's epilogue drains its own 128 TMEM lanes; the follower's warps arrive remotely on the leader's
+//     accumulator-free barrier (16 arrivals)
+#if FCEST_OZAKI_KB == 64
+constexpr int HALF_BYTES = TILE_BYTES / 2;          // 64 rows x 64 bytes
+constexpr int NSLOT2 = 224 * 1024 / HALF_BYTES;     // 56 slots of 4 KB: an A tile takes two, a B half tile one
+constexpr int NBAR2 = 8, NBAR2_LOG = 3;
+constexpr uint32_t kInstrDesc2 =
+    (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+
+template <int NS>
+struct Sched2 : Sched<NS> {
+  // K blocks per stage: up to 72 KB per CTA (three stages in flight)
+  __host__ __device__ static constexpr int kbs(int p) { return Sched<NS>::nsl(p) <= 3 ? 6 / Sched<NS>::nsl(p) : 1; }
+};
+// slots of a stage of g K blocks: all A tiles (2 slots each), then all B half tiles; even, so that an A tile never
+// straddles the end of the ring
+__host__ __device__ __forceinline__ uint32_t stage_slots2(int nsl, int g) { return (uint32_t)((3 * nsl * g + 1) & ~1); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <int NS, int P>
+__device__ __forceinline__ void mma_stage_pair(uint32_t lo0, uint32_t a_pos, uint32_t b_pos, uint32_t tmem_base,
+                                               uint32_t first_kb) {
+  using S = Sched<NS>;
+  constexpr int nsl = S::nsl(P), d_hi = S::d_hi(P), d_lo = S::d_lo(P);
+  constexpr uint64_t hi = ((uint64_t)((8 * KB) >> 4) | ((uint64_t)1 << 14) | ((uint64_t)4 << 29)) << 32;
+  uint32_t b_lo[nsl];
+#pragma unroll
+  for (int t = 0; t < nsl; ++t) {
+    uint32_t slot = b_pos + t;
+    slot = slot >= NSLOT2 ? slot - NSLOT2 : slot;
+    b_lo[t] = lo0 + slot * (HALF_BYTES >> 4);
+  }
+#pragma unroll
+  for (int s = 0; s < nsl; ++s) {
+    uint32_t slot = a_pos + 2 * s;
+    slot = slot >= NSLOT2 ? slot - NSLOT2 : slot;
+    const uint32_t a_lo = lo0 + slot * (HALF_BYTES >> 4);
+#pragma unroll
+    for (int t = 0; t < nsl; ++t) {
+      if (s + t < d_lo || s + t > d_hi) continue;
+      const uint32_t acc = tmem_base + (uint32_t)((d_hi - (s + t)) * TN);
+      const uint32_t keep = s > 0 ? 1u : (first_kb ? 0u : 1u);
+      umma_i8_pair(acc, hi | a_lo, hi | b_lo[t], kInstrDesc2, keep);
+      umma_i8_pair(acc, hi | (a_lo + 2), hi | (b_lo[t] + 2), kInstrDesc2, 1u);   // second K = 32 step: +32 bytes
+    }
+  }
+}
+
+template <int NS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+ozaki_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using S = Sched2<NS>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ long long t_done_s;   // diagnostics only
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + NSLOT2 * HALF_BYTES;
+  const uint32_t full = bars, empty = bars + 8 * NBAR2, tfull = empty + 8 * NBAR2, tempty = tfull + 32, tptr = tempty + 32;
+  static_assert(16 * NBAR2 + 64 + 8 <= SMEM_BAR, "barrier area");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int rows2 = p.tiles_m >> 1;                  // 256-row tile rows
+  const int tiles2 = rows2 * p.tiles_n;
+  const int units = tiles2 * p.ksplit;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NBAR2; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(tfull + 8 * i, 1); mbar_init(tempty + 8 * i, 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer's barriers are initialised before anything of ours can signal them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+  const bool dbg = p.dbg != nullptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs, same schedule) =============================
+    uint32_t seq = 0, tail = 0, pos = 0, free_slots = NSLOT2;
+    unsigned long long sizes = 0;   // 8 bits per in-flight stage
+    long long w_e = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    const uint32_t full_leader = mapa_cta(full, 0);
+    for (int u = pair; u < units; u += npairs) {
+      const int ks = u / tiles2, tile2 = u - ks * tiles2;
+      const int tn = tile2 / rows2, tm = 2 * (tile2 - tn * rows2) + (int)rank;
+      const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
+#pragma unroll
+      for (int ps = 0; ps < S::NPASS; ++ps) {
+        const int nsl = S::nsl(ps);
+        for (int kb = kb0; kb < kb1; kb += S::kbs(ps)) {
+          const int g = kb1 - kb < S::kbs(ps) ? kb1 - kb : S::kbs(ps);
+          const uint32_t n = stage_slots2(nsl, g);
+          while (free_slots < n || seq - tail >= (uint32_t)NBAR2) {
+            mbar_wait_t(empty + 8 * (tail & (NBAR2 - 1)), (tail >> NBAR2_LOG) & 1u, w_e, dbg);
+            free_slots += (uint32_t)((sizes >> (8 * (tail & (NBAR2 - 1)))) & 255ull);
+            ++tail;
+          }
+          const uint32_t sh = 8 * (seq & (NBAR2 - 1));
+          sizes = (sizes & ~(255ull << sh)) | ((unsigned long long)n << sh);
+          free_slots -= n;
+          if (elect_one()) {
+            const uint32_t fb = full_leader + 8 * (seq & (NBAR2 - 1));
+            if (leader) mbar_expect_tx(full + 8 * (seq & (NBAR2 - 1)), 2u * 3u * (uint32_t)(nsl * g) * (uint32_t)HALF_BYTES);
+            for (int j = 0; j < g; ++j) {
+              for (int s = 0; s < nsl; ++s) {
+                uint32_t slot = pos + (uint32_t)(2 * (j * nsl + s));
+                slot = slot >= NSLOT2 ? slot - NSLOT2 : slot;
+                tma_load_2d_pair(base + slot * HALF_BYTES, &tmA, fb, 0, ((s * p.nkb + kb + j) * p.tiles_m + tm) * 4);
+              }
+              for (int t = 0; t < nsl; ++t) {
+                uint32_t slot = pos + (uint32_t)(2 * nsl * g + j * nsl + t);
+                slot = slot >= NSLOT2 ? slot - NSLOT2 : slot;
+                tma_load_2d_pair(base + slot * HALF_BYTES, &tmB, fb, 0, ((t * p.nkb + kb + j) * p.tiles_n + tn) * 4 + 2 * (int)rank);
+              }
+            }
+          }
+          __syncwarp();
+          pos += n;
+          pos = pos >= NSLOT2 ? pos - NSLOT2 : pos;
+          ++seq;
+        }
+      }
+    }
+    if (dbg && lane == 0) {
+      p.dbg[8 * blockIdx.x + 0] = clock64() - t_begin;
+      p.dbg[8 * blockIdx.x + 1] = w_e;
+    }
+  } else if (warp == 1 || warp == 10) {
+    if (leader) {
+      // ===================================== MMA issuers (leader CTA): two warps take alternate stages ==========
+      const uint32_t me = warp == 1 ? 0u : 1u;
+      uint32_t seq = 0, pos = 0;
+      uint32_t use0 = 0, use1 = 0, use2 = 0, use3 = 0;
+      long long w_f = 0, w_te = 0, w_op = 0, w_busy = 0;
+      const long long t_begin = dbg ? clock64() : 0;
+      const uint32_t lo0 = ((base & 0x3FFFFu) >> 4) | (1u << 16);
+      for (int u = pair; u < units; u += npairs) {
+        const int ks = u / tiles2;
+        const int kb0 = (int)((long long)ks * p.nkb / p.ksplit), kb1 = (int)((long long)(ks + 1) * p.nkb / p.ksplit);
+#pragma unroll
+        for (int ps = 0; ps < S::NPASS; ++ps) {
+          const int nbuf = S::d_hi(ps) - S::d_lo(ps) + 1;
+          const int nsl = S::nsl(ps);
+          for (int kb = kb0; kb < kb1; kb += S::kbs(ps)) {
+            const int g = kb1 - kb < S::kbs(ps) ? kb1 - kb : S::kbs(ps);
+            const uint32_t n = stage_slots2(nsl, g);
+            if ((seq & 1u) == me) {
+              if (kb == kb0) {   // first stage of the pass: both CTAs' epilogues have drained its accumulators
+                const long long t0 = dbg ? clock64() : 0;
+                if (nbuf > 0) mbar_wait_cluster(tempty + 0, (use0 & 1u) ^ 1u);
+                if (nbuf > 1) mbar_wait_cluster(tempty + 8, (use1 & 1u) ^ 1u);
+                if (nbuf > 2) mbar_wait_cluster(tempty + 16, (use2 & 1u) ^ 1u);
+                if (nbuf > 3) mbar_wait_cluster(tempty + 24, (use3 & 1u) ^ 1u);
+                if (dbg) w_te += clock64() - t0;
+              }
+              mbar_wait_t(full + 8 * (seq & (NBAR2 - 1)), (seq >> NBAR2_LOG) & 1u, w_f, dbg);
+              const long long t_ready = dbg ? clock64() : 0;
+              if (seq > 0) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");
+              long long t_i0 = 0;
+              if (dbg) {
+                const long long td = *reinterpret_cast<volatile long long*>(&t_done_s);
+                if (seq > 0 && t_ready > td) w_op += t_ready - td;
+                t_i0 = clock64();
+              }
+              tc_fence_after();
+              if (elect_one()) {
+                for (int j = 0; j < g; ++j) {
+                  uint32_t a_pos = pos + (uint32_t)(2 * j * nsl), b_pos = pos + (uint32_t)(2 * nsl * g + j * nsl);
+                  a_pos = a_pos >= NSLOT2 ? a_pos - NSLOT2 : a_pos;
+                  b_pos = b_pos >= NSLOT2 ? b_pos - NSLOT2 : b_pos;
+                  if (ps == 0) mma_stage_pair<NS, 0>(lo0, a_pos, b_pos, tmem_base, kb + j == kb0);
+                  else mma_stage_pair<NS, (S::NPASS > 1 ? 1 : 0)>(lo0, a_pos, b_pos, tmem_base, kb + j == kb0);
+                }
+                tc_commit_pair(empty + 8 * (seq & (NBAR2 - 1)));
+                if (kb + g == kb1) {
+                  if (nbuf > 0) tc_commit_pair(tfull + 0);
+                  if (nbuf > 1) tc_commit_pair(tfull + 8);
+                  if (nbuf > 2) tc_commit_pair(tfull + 16);
+                  if (nbuf > 3) tc_commit_pair(tfull + 24);
+                }
+              }
+              __syncwarp();
+              if (dbg) {
+                const long long t1 = clock64();
+                w_busy += t1 - t_i0;
+                if (lane == 0) *reinterpret_cast<volatile long long*>(&t_done_s) = t1;
+              }
+              asm volatile("bar.arrive %0, 64;" ::"r"(1u + (seq & 1u)) : "memory");
+            }
+            pos += n;
+            pos = pos >= NSLOT2 ? pos - NSLOT2 : pos;
+            ++seq;
+          }
+          if (nbuf > 0) ++use0;
+          if (nbuf > 1) ++use1;
+          if (nbuf > 2) ++use2;
+          if (nbuf > 3) ++use3;
+        }
+      }
+      if (seq > 0 && ((seq - 1u) & 1u) != me) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");
+      if (dbg && lane == 0) {
+        if (me == 0) p.dbg[8 * blockIdx.x + 3] = clock64() - t_begin;
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 2), (unsigned long long)w_busy);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 4), (unsigned long long)w_op);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 6), (unsigned long long)w_te);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 8 * blockIdx.x + 7), (unsigned long long)w_f);
+      }
+    }
+  } else {
+    // ===================================== epilogue warps (each CTA drains its own 128 rows) ==================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int rloc = q * 32 + lane;
+    uint32_t use[4] = {0, 0, 0, 0};
+    const uint32_t tempty_leader = mapa_cta(tempty, 0);
+    for (int u = pair; u < units; u += npairs) {
+      const int ks = u / tiles2, tile2 = u - ks * tiles2;
+      const int tn = tile2 / rows2, tm = 2 * (tile2 - tn * rows2) + (int)rank;
+      const int tile = tn * p.tiles_m + tm;
+      double acc[64];
+#pragma unroll
+      for (int ps = 0; ps < S::NPASS; ++ps) {
+#pragma unroll
+        for (int d = S::d_hi(ps); d >= S::d_lo(ps); --d) {
+          const int b = S::d_hi(ps) - d;
+          const bool first = ps == 0 && d == S::d_hi(0);
+          mbar_wait(tfull + 8 * b, use[b] & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TN + half * 64 + c * 32), v);
+            tmem_ld_wait();
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = i32_to_f64(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fma(acc[c * 32 + j], 0.00390625, i32_to_f64(v[j]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * b);
+          ++use[b];
+        }
+      }
+      const int row = tm * TM + rloc;
+      const int col0 = tn * TN + half * 64;
+      if (p.ksplit == 1) {
+        if (row < p.M) {
+          const double sr = p.rsA[row] * p.alpha;
+          const double br = p.bias_row ? p.bias_row[row] : 0.0;
+          double* crow = p.C + (long long)row * p.ldc;
+          if (col0 + 64 <= p.N && ((p.ldc & 1) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              const double2 sc = *reinterpret_cast<const double2*>(p.rsB + col0 + j);
+              double2 o;
+              o.x = acc[j] * sr * sc.x + br;
+              o.y = acc[j + 1] * sr * sc.y + br;
+              *reinterpret_cast<double2*>(crow + col0 + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < p.N) crow[col0 + j] = acc[j] * sr * p.rsB[col0 + j] + br;
+          }
+        }
+      } else {
+        double* dst = p.partial + ((long long)ks * (p.tiles_m * p.tiles_n) + tile) * (TM * TN) + rloc * TN + half * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(acc[j], acc[j + 1]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer may still signal our barriers / read our shared memory until it is done too
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+#endif  // FCEST_OZAKI_KB == 64
 
 // Sum of the K-split partials in fixed order, exponent scaling, bias.  grid (tiles, 16), 256 threads: 8 rows x 128 cols.
 __global__ void __launch_bounds__(256) ozaki_fixup_kernel(const Params p) {
@@ -712,25 +1092,44 @@ static long long* g_debug_counters = nullptr;
 static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 struct Plan {
-  int Mp, Np, tiles_m, tiles_n, nkb, ksplit;
+  int Mp, Np, tiles_m, tiles_n, nkb, ksplit, pair;
   long long offA, offB, off_rsA, off_rsB, off_E, off_part, total;
 };
 
+// CTA-pair kernel (256-row tiles): opt-in with FCEST_OZAKI_PAIR=1 (read once).  Measured at the three C4 shapes it is
+// parity-green and within -2 % ... +4 % of the single-CTA kernel (profiles/r02_ncu_ozaki.md), so the default stays single.
+static bool use_pair(int M) {
+#if FCEST_OZAKI_KB == 64
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("FCEST_OZAKI_PAIR");
+    forced = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  (void)M;
+  return forced == 1;
+#else
+  (void)M;
+  return false;
+#endif
+}
+
 static Plan make_plan(int M, int N, int K, int ns, int sms) {
   Plan pl;
-  pl.Mp = (int)round_up(M, TM);
+  pl.pair = use_pair(M) ? 1 : 0;
+  pl.Mp = (int)round_up(M, pl.pair ? 2 * TM : TM);
   pl.Np = (int)round_up(N, TN);
   pl.tiles_m = pl.Mp / TM;
   pl.tiles_n = pl.Np / TN;
   pl.nkb = (int)((K + KB - 1) / KB);
   const int tiles = pl.tiles_m * pl.tiles_n;
+  if (pl.pair) sms /= 2;   // work units are 256 x 128 tiles dealt to CTA pairs
   // K split: fewest splits within 3 % of the best wave efficiency; every unit keeps >= 512 and at most 16384 contraction steps
   // (int32 accumulators: 7 pairs x 16384 terms x 127^2 < 2^31)
   int ks_min = (pl.nkb * KB + 16383) / 16384, best = ks_min;
   double best_cost = 1e300;
   for (int ks = ks_min; ks <= 16; ++ks) {
     if (ks > ks_min && pl.nkb * KB / 64 / ks < 8) break;
-    const double cost = (double)((tiles * (long long)ks + sms - 1) / sms) / ks;
+    const double cost = (double)(((tiles >> pl.pair) * (long long)ks + sms - 1) / sms) / ks;
     if (cost < best_cost * 0.97) { best_cost = cost; best = ks; }
   }
   pl.ksplit = best < 1 ? 1 : best;
@@ -808,6 +1207,60 @@ static int launch_gemm(const Params& p, int grid, cudaStream_t stream) {
   FCEST_CHECK_LAUNCH();
   return 0;
 }
+
+#if FCEST_OZAKI_KB == 64
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// digit array of `bytes` bytes seen as rows of 256 x 8 bytes; box = `box_rows` rows (4 = one 8 KB tile, 2 = half a tile),
+// no swizzle (the tiles are stored pre-swizzled)
+static int make_map(CUtensorMap* map, const void* base, long long bytes, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return FCEST_ERR_UNSUPPORTED;
+  const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 2048)};
+  const cuuint64_t strides[1] = {2048};
+  const cuuint32_t box[2] = {256, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : FCEST_ERR_ARGUMENT;
+}
+
+template <int NS>
+static int launch_gemm_pair(const Params& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_pair_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, p.dA, (long long)p.ns * p.nkb * p.tiles_m * TILE_BYTES, 4);
+  if (rc) return rc;
+  rc = make_map(&tmB, p.dB, (long long)p.ns * p.nkb * p.tiles_n * TILE_BYTES, 2);
+  if (rc) return rc;
+  const bool prof = g_prof_on && g_prof_n < PROF_MAX;
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n][0], stream);
+  ozaki_gemm_pair_kernel<NS><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  if (prof) cudaEventRecord(g_prof_ev[g_prof_n++][1], stream);
+  FCEST_CHECK_LAUNCH();
+  return 0;
+}
+#endif
 
 // Back-to-back tcgen05.mma kind::i8 (M 128, N 128, K 32) on zero operands: the issue-rate ceiling of the int8 tensor pipe
 // (64 cycles per instruction, tools/microbench/umma_rate.cu); bench.py times it with CUDA events as the roofline peak.
@@ -919,16 +1372,32 @@ extern "C" int fcest_dgemm_ozaki(int a_kmajor, int b_kmajor, int M, int N, int K
   p.dA = dA;
   p.dB = dB;
   p.dbg = oz::g_debug_counters;
-  const int units = pl.tiles_m * pl.tiles_n * pl.ksplit;
-  const int grid = units < sms ? units : sms;
   rc = FCEST_ERR_ARGUMENT;
-  switch (slices) {
-    case 2: rc = oz::launch_gemm<2>(p, grid, stream); break;
-    case 3: rc = oz::launch_gemm<3>(p, grid, stream); break;
-    case 4: rc = oz::launch_gemm<4>(p, grid, stream); break;
-    case 5: rc = oz::launch_gemm<5>(p, grid, stream); break;
-    case 6: rc = oz::launch_gemm<6>(p, grid, stream); break;
-    case 7: rc = oz::launch_gemm<7>(p, grid, stream); break;
+#if FCEST_OZAKI_KB == 64
+  if (pl.pair) {
+    const int units2 = (pl.tiles_m / 2) * pl.tiles_n * pl.ksplit;
+    const int grid = 2 * (units2 < sms / 2 ? units2 : sms / 2);
+    switch (slices) {
+      case 2: rc = oz::launch_gemm_pair<2>(p, grid, stream); break;
+      case 3: rc = oz::launch_gemm_pair<3>(p, grid, stream); break;
+      case 4: rc = oz::launch_gemm_pair<4>(p, grid, stream); break;
+      case 5: rc = oz::launch_gemm_pair<5>(p, grid, stream); break;
+      case 6: rc = oz::launch_gemm_pair<6>(p, grid, stream); break;
+      case 7: rc = oz::launch_gemm_pair<7>(p, grid, stream); break;
+    }
+  } else
+#endif
+  {
+    const int units = pl.tiles_m * pl.tiles_n * pl.ksplit;
+    const int grid = units < sms ? units : sms;
+    switch (slices) {
+      case 2: rc = oz::launch_gemm<2>(p, grid, stream); break;
+      case 3: rc = oz::launch_gemm<3>(p, grid, stream); break;
+      case 4: rc = oz::launch_gemm<4>(p, grid, stream); break;
+      case 5: rc = oz::launch_gemm<5>(p, grid, stream); break;
+      case 6: rc = oz::launch_gemm<6>(p, grid, stream); break;
+      case 7: rc = oz::launch_gemm<7>(p, grid, stream); break;
+    }
   }
   if (rc) return rc;
   if (pl.ksplit > 1) {

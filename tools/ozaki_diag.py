@@ -30,7 +30,10 @@ a.record(); ops.dgemm_ozaki(*args, out, slices=ns); b.record()
 torch.cuda.synchronize()
 lib.fcest_dgemm_ozaki_debug(None)
 c = cnt.view(148, 8).double().cpu()
-names = ["producer total", "producer wait empty", "-", "mma total", "mma wait full", "-", "mma wait tmem_empty"]
-print(which, "slices", ns, "ms", a.elapsed_time(b))
+names = ["producer total", "producer wait empty", "issue busy (both issuers)", "mma total",
+         "operands later than issue", "-", "mma wait tmem_empty", "wait full (both issuers)"]
+print(which, "slices", ns, "ms", a.elapsed_time(b), "pair" if os.environ.get("FCEST_OZAKI_PAIR") == "1" else "")
+c = c[c[:, 3] > 0]   # CTAs that issued MMAs (pair kernel: leaders only)
 for i, n in enumerate(names):
-    print(f"  {n:24s} mean {c[:, i].mean():12.0f}  min {c[:, i].min():12.0f}  max {c[:, i].max():12.0f} cycles")
+    if n != "-":
+        print(f"  {n:28s} mean {c[:, i].mean():12.0f}  min {c[:, i].min():12.0f}  max {c[:, i].max():12.0f} cycles")
