@@ -37,4 +37,10 @@ int launch_loglik_tiles(LikParams p, cudaStream_t stream, int* part_rows);
 bool loglik_tiles_supported(int D, int nu);
 long long loglik_tiles_scratch_bytes(int D, int nu);
 
+// Cluster-tiled variant (likelihood_cluster.cu), 8 <= D <= 407: one thread-block cluster per matrix, the factor's
+// tiles in the distributed shared memory of the cluster.  p.ws must point to loglik_cluster_scratch_bytes(D, nu) bytes.
+int launch_loglik_cluster(LikParams p, cudaStream_t stream, int* part_rows);
+bool loglik_cluster_supported(int D, int nu);
+long long loglik_cluster_scratch_bytes(int D, int nu);
+
 }  // namespace fcest

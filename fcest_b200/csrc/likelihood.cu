@@ -294,6 +294,7 @@ static const int kBigCtas = 148 * 3;
 extern "C" long long fcest_wishart_loglik_scratch_bytes(int D, int nu) {
   long long need = 0;
   if (!loglik_warp_supported(D, nu) && loglik_tiles_supported(D, nu)) need = loglik_tiles_scratch_bytes(D, nu);
+  if (loglik_cluster_supported(D, nu) && loglik_cluster_scratch_bytes(D, nu) > need) need = loglik_cluster_scratch_bytes(D, nu);
   if (fcest_wishart_loglik_smem_bytes(D, nu) > 227 * 1024) {
     const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
     const long long stride = (long long)Dp * pitch4(Np) + (long long)Dp * pitch4(Dp) + 12LL * Dp;
@@ -326,10 +327,17 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   // kernels of this file (shared memory for D <= ~80, L2 scratch above)
   static const bool force_cta = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cta"); }();
   static const bool force_warp = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "warp"); }();
+  static const bool force_cluster = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cluster"); }();
   bool launched = false;
   int part_rows = N;  // rows of the A_bar / lam_bar partial workspaces that the kernel filled
   // D <= 7: sub-warp kernel (likelihood_subwarp.cu): four problems per warp, registers and shuffles only
-  if (!force_cta && !force_warp && loglik_subwarp_supported(D, nu)) {
+  // FCEST_LIK_IMPL=cluster: the cluster-tiled kernel at any size it supports (A/B runs against the tiles kernel)
+  if (force_cluster && loglik_cluster_supported(D, nu) && scratch != nullptr) {
+    const int rc = launch_loglik_cluster(p, stream, &part_rows);
+    if (rc > 0) return rc;
+    launched = (rc == 0);
+  }
+  if (!launched && !force_cta && !force_warp && loglik_subwarp_supported(D, nu)) {
     const int rc = launch_loglik_subwarp(p, stream, &part_rows);
     if (rc > 0) return rc;
     launched = (rc == 0);
@@ -342,6 +350,13 @@ extern "C" int fcest_wishart_loglik(const double* fmean, const double* fvar, lon
   // 56 <= D <= 207: shared-memory-tiled CTA-per-matrix kernel (likelihood_tiles.cu)
   if (!launched && !force_cta && loglik_tiles_supported(D, nu) && scratch != nullptr) {
     const int rc = launch_loglik_tiles(p, stream, &part_rows);
+    if (rc > 0) return rc;
+    launched = (rc == 0);
+  }
+  // 208 <= D <= 407: cluster-tiled kernel (likelihood_cluster.cu): the factor's tiles in the distributed shared memory
+  // of a thread-block cluster
+  if (!launched && !force_cta && loglik_cluster_supported(D, nu) && scratch != nullptr) {
+    const int rc = launch_loglik_cluster(p, stream, &part_rows);
     if (rc > 0) return rc;
     launched = (rc == 0);
   }

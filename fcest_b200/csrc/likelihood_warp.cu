@@ -493,6 +493,8 @@ int launch_loglik_warp(const LikParams& p, cudaStream_t stream, int* part_rows) 
   if (!loglik_warp_supported(p.D, p.nu)) return -1;
   const int NB = p.D / 8 + 1;
   int W = p.S < 8 ? p.S : 8;
+  static const int forced_w = getenv("FCEST_LIK_WARPS") ? atoi(getenv("FCEST_LIK_WARPS")) : 0;  // A/B runs
+  if (forced_w > 0 && forced_w < W) W = forced_w;
   if (p.D > 32 * W) W = (p.D + 31) / 32;  // phase D keeps one lam_bar element per thread
   while (W > 1 && wl_smem_bytes(NB, p.nu, W) > kSmemLimit) --W;
   const long long smem = wl_smem_bytes(NB, p.nu, W);
