@@ -1,29 +1,36 @@
 // Cluster-tiled Wishart likelihood (forward + analytic backward) for 208 <= D <= 407: one thread-block CLUSTER per
 // D x D problem, the Cholesky factor held as packed lower 8 x 8 tiles in the DISTRIBUTED shared memory of the
-// cluster's C CTAs (679 KB of tiles at D = 400: 170 - 180 KB per SM in a cluster of four).
+// cluster's C CTAs (679 KB of tiles at D = 400: 170 - 180 KB per SM in a cluster of four; CTA pairs up to D = 303).
 //
 // Reference semantics: fcest/models/likelihoods.py:126-206, :253-264 (any D: `tf.linalg.cholesky` at :185); the math
 // (bordered y row with unit pivot, Q'' = Sigma^-1 G - alpha (alpha^T G) out of the substitution, the lam_bar identity)
 // is the one of likelihood_warp.cu / likelihood_tiles.cu.
 //
-// Mapping (C = 4 CTAs x 8 warps = 32 warps per problem):
+// Mapping (C CTAs x 8 warps per problem):
 //   * tile (ib, jb) of the lower triangle lives in the shared memory of CTA  ib mod C  (block rows dealt cyclically,
 //     packed per CTA); every CTA reaches every tile through the cluster's shared-memory window (generic pointers from
 //     `mapa`), so all DMMA operands of the O(D^3) phases come from on-chip memory of the cluster;
-//   * P0  per time step: am = A o fmean, as = A o sqrt(fvar) into the cluster's global slot (L2);
-//   * P1  Sigma = G G^T: output-stationary 16 x 16 macro tiles in registers, dealt over the 32 warps; G streamed through
-//         a double-buffered 4-column (one DMMA k-step) shared-memory panel that every CTA builds for itself from am, as
-//         and the noise; finished tiles are stored into their owner's shared memory;
+//   * P0  per sample: G = A o (fmean + sqrt(fvar) o eps) once, coalesced, into the cluster's global slot (L2 resident);
+//   * P1  Sigma = G G^T: output-stationary 16 x 16 macro tiles in registers, dealt over the cluster's warps; G arrives as
+//         4-column panels (one DMMA k-step; dense 32-byte rows are conflict-free for the fragment reads) through a ring
+//         of TMA tensor-map copies (`cp.async.bulk.tensor.3d`, SASS UTMALDG; rows >= D zero-filled by the copy engine)
+//         with full / empty mbarriers -- no registers and no block barrier in the k loop; finished tiles are stored into
+//         their owner's shared memory;
 //   * P2  left-looking blocked Cholesky: every CTA updates the tiles of ITS block rows (its own operand rows are local,
-//         the tiles of block row jb come from their owner); the owner of row jb factors + inverts the diagonal tile
-//         (lik_tiles.cuh); two cluster barriers per block column;
-//   * P4  per 8-column block of G one warp (32 at a time): right-looking block forward substitution, row D negated,
-//         right-looking back substitution with all row tiles of the column block in registers; the per-sample cotangents
+//         the tiles of block row jb come from their owner; two partial sums halve the dependent DMMA chain); the owner
+//         of row jb factors + inverts the diagonal tile (lik_tiles.cuh); two cluster barriers per block column;
+//   * P4  per 8-column block of G one warp: right-looking block forward substitution, row D negated, right-looking
+//         back substitution with all row tiles of the column block in registers; operand fragments are requested a
+//         chunk ahead of their DMMAs (explicit software pipeline over the cluster window); the per-sample cotangents
 //         accumulate in the cluster's global slot (U1, U2);
 //   * P5  lam_bar, ve on CTA 0 (row sums and alpha arrive through the cluster window).
-// The noise panels of the NEXT k-steps are pulled with `cp.async.bulk.prefetch.L2` (the bulk-copy engine) one sample ahead.
+// The noise of the NEXT sample is pulled into L2 with `cp.async.bulk.prefetch.L2` while the current one is factored.
+// What bounds it: the cluster window delivers ~20 B/clk per SM (B300_MICROARCH.md), a quarter-tile DMMA operand is 256 B,
+// so with 1/2 (pairs) or 3/4 (clusters of four) of the operands remote the substitution cannot exceed ~40 % / ~30 % of
+// the DMMA issue rate; measured 16.5 % (D = 256, pairs) and 11 % (clusters of four) of the fp64 peak.
 // Deterministic: every accumulation has a fixed owner and order.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -40,12 +47,12 @@ namespace fcest {
 constexpr int CL_WARPS = 8;   // warps per CTA
 constexpr int CL_MQ = 6;      // macro tiles per warp and SYRK pass
 constexpr int CL_PC = 4;      // columns of a G panel = one DMMA k-step (pitch 4: fragment reads are contiguous)
-constexpr int CL_PE = 7;      // panel elements per thread: 407 * 4 / 256 <= 7
+constexpr int CL_MAXST = 8;   // at most 8 panel stages
 constexpr int CL_PF = 3;      // G tiles in flight ahead of the forward substitution
 
 struct ClLayout {
-  int NB, Dp, Dm, maxt;
-  int off_pan, off_vec, total;  // doubles
+  int NB, Dp, Dm, maxt, ST;
+  int off_pan, off_vec, off_bar, total;  // doubles
 };
 
 // packed offset (in tiles) of tile (ib, jb) inside its owner CTA  ib % C
@@ -56,8 +63,8 @@ __host__ __device__ __forceinline__ int cl_loff(int ib, int jb) {
 }
 
 template <int C>
-__host__ __device__ inline ClLayout cl_layout(int NB) {
-  ClLayout L;
+__host__ __device__ constexpr ClLayout cl_layout(int NB) {
+  ClLayout L = {};
   L.NB = NB;
   L.Dp = 8 * NB;
   L.Dm = (L.Dp + 15) / 16 * 16;
@@ -68,11 +75,49 @@ __host__ __device__ inline ClLayout cl_layout(int NB) {
     if (t > L.maxt) L.maxt = t;
   }
   L.off_pan = L.maxt * 64;
-  int pan = 2 * L.Dm * CL_PC;                        // two panel buffers (P1); reused as 8 x Dp row-sum partials (P4)
-  if (pan < CL_WARPS * L.Dp) pan = CL_WARPS * L.Dp;
-  L.off_vec = L.off_pan + pan;
-  L.total = L.off_vec + 4 * L.Dp + 32;               // dinv, yv, spl, alpha, misc (bad flags of the C CTAs)
+  const int vec = 4 * L.Dp + 32;                      // dinv, yv, spl, alpha, misc (bad flags of the C CTAs)
+  const int stage = L.Dm * CL_PC;                     // one panel: Dm rows x 4 columns
+  const int avail = 227 * 1024 / 8 - 16 - L.off_pan - vec - 2 * CL_MAXST;
+  int st = avail / stage;
+  if (st > CL_MAXST) st = CL_MAXST;
+  if (st < 2) st = 2;
+  while (st * stage < CL_WARPS * L.Dp) ++st;          // the ring doubles as 8 x Dp row-sum partials in P4
+  L.ST = st;
+  L.off_vec = L.off_pan + st * stage;
+  L.off_bar = L.off_vec + vec;
+  L.total = L.off_bar + 2 * CL_MAXST;
   return L;
+}
+
+__device__ __forceinline__ void cl_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void cl_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA tensor-map copy of one box (4 columns x BH rows of one cluster's G slot) global -> shared (SASS UTMALDG)
+__device__ __forceinline__ void cl_tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 __device__ __forceinline__ void cl_cvt_c_to_b(double c0, double c1, int gid, int tig, double& b0, double& b1) {
@@ -86,8 +131,9 @@ __device__ __forceinline__ void cl_cvt_c_to_b(double c0, double c1, int gid, int
 template <int C>
 struct ClCtx {
   const double* rb[C];   // tile store of every CTA of the cluster (generic pointers into the cluster window)
-  const double* am; const double* as_; const double* ep;
-  int D, nu, colC, ycol, gid, tig, oA0, oA1, oT0, oT1;
+  const double* G; const double* ep;   // G slot (row pitch ldgs), noise of this sample
+  int D, nu, ldgs, colC, ycol, gid, tig, oA0, oA1, oT0, oT1;
+  int kb_start;          // first block row with a non-zero right-hand side (> 0 only for the column block that holds just e_D)
 };
 
 template <int C, int IB, int JB>
@@ -104,59 +150,116 @@ __device__ __forceinline__ void cl_load_g(const ClCtx<C>& c, int ib, double (&g)
   for (int e = 0; e < 2; ++e) {
     const int k = c.colC + e;
     double v = 0.0;
-    if (d < c.D && k < c.nu) { const int r = d * c.nu + k; v = c.am[r] + c.as_[r] * __ldg(c.ep + r); }
+    if (d < c.D && k < c.nu) v = c.G[d * c.ldgs + k];
     else if (d == c.D && k == c.ycol) v = 1.0;
     g[e] = v;
   }
 }
 
-template <int NB, int C, int KB, int IB>
-__device__ __forceinline__ void cl_trail_fwd(double (&acc)[NB][2], const ClCtx<C>& c, int off, double b) {
-  if constexpr (IB < NB) {
-    dmma(acc[IB][0], acc[IB][1], cl_tile<C, IB, KB>(c)[off], b);
-    cl_trail_fwd<NB, C, KB, IB + 1>(acc, c, off, b);
-  }
+// Operand fragments come from the cluster window (generic loads, a few hundred cycles from a peer SM), so the trailing
+// updates run as an explicit software pipeline: volatile loads keep program order, CL_W fragments are requested one
+// chunk ahead of the DMMAs that use them (a ring of 2 CL_W registers), and the first chunk is requested before the
+// shuffles / diagonal-tile products of the step, which do not depend on it.
+template <int NB> constexpr int cl_w() { return NB > 40 ? 6 : 12; }   // fewer registers where 2 NB accumulators are > 80
+
+__device__ __forceinline__ double cl_ldv(const double* ptr) {
+  double v;
+  asm volatile("ld.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  return v;
 }
-template <int NB, int C, int KB, int IB>
-__device__ __forceinline__ void cl_trail_bwd(double (&acc)[NB][2], const ClCtx<C>& c, int off, double b) {
-  if constexpr (IB < KB) {
-    dmma(acc[IB][0], acc[IB][1], cl_tile<C, KB, IB>(c)[off], b);
-    cl_trail_bwd<NB, C, KB, IB + 1>(acc, c, off, b);
+
+template <int NB, int C, int KB, bool FWD>
+struct ClTrail {
+  static constexpr int CL_W = cl_w<NB>();
+  static constexpr int M = FWD ? NB - KB - 1 : KB;   // tiles below (forward) / left of (backward) the diagonal tile
+  static constexpr int n = 2 * M;                    // first all tiles with the first half fragment, then the second
+  template <int I>
+  static __device__ __forceinline__ const double* ptr(const ClCtx<C>& c) {
+    constexpr int row = I % (M > 0 ? M : 1), half = I / (M > 0 ? M : 1);
+    if constexpr (FWD) return cl_tile<C, KB + 1 + row, KB>(c) + (half ? c.oA1 : c.oA0);
+    else return cl_tile<C, KB, row>(c) + (half ? c.oT1 : c.oT0);
   }
-}
-// forward, right-looking: H[kb] = I_kb (G[kb] + acc[kb]); acc[ib] -= L[ib][kb] H[kb] (ib > kb)
+  template <int I, int E>
+  static __device__ __forceinline__ void load(double (&buf)[2 * CL_W], const ClCtx<C>& c) {
+    if constexpr (I < E && I < n) {
+      buf[I % (2 * CL_W)] = cl_ldv(ptr<I>(c));
+      load<I + 1, E>(buf, c);
+    }
+  }
+  template <int I, int E>
+  static __device__ __forceinline__ void mma(double (&acc)[NB][2], const double (&buf)[2 * CL_W], double b0, double b1) {
+    if constexpr (I < E && I < n) {
+      constexpr int row = I % (M > 0 ? M : 1), half = I / (M > 0 ? M : 1);
+      constexpr int IB = FWD ? KB + 1 + row : row;
+      dmma(acc[IB][0], acc[IB][1], buf[I % (2 * CL_W)], half ? b1 : b0);
+      mma<I + 1, E>(acc, buf, b0, b1);
+    }
+  }
+  template <int S>
+  static __device__ __forceinline__ void run(double (&acc)[NB][2], double (&buf)[2 * CL_W], const ClCtx<C>& c, double b0,
+                                             double b1) {
+    if constexpr (S < n) {
+      load<S + CL_W, S + 2 * CL_W>(buf, c);
+      mma<S, S + CL_W>(acc, buf, b0, b1);
+      run<S + CL_W>(acc, buf, c, b0, b1);
+    }
+  }
+};
+
+// forward, right-looking: H[kb] = I_kb (G[kb] + acc[kb]); acc[ib] -= L[ib][kb] H[kb] (ib > kb); ik = fragments of the
+// diagonal tile of this step (requested one step ahead)
 template <int NB, int C, int KB>
-__device__ __forceinline__ void cl_fwd(double (&acc)[NB][2], double (&gq)[CL_PF][2], const ClCtx<C>& c) {
+__device__ __forceinline__ void cl_fwd(double (&acc)[NB][2], double (&gq)[CL_PF][2], double (&ik)[2], const ClCtx<C>& c) {
   if constexpr (KB < NB) {
-    double b0, b1;
-    cl_cvt_c_to_b(acc[KB][0] + gq[KB % CL_PF][0], acc[KB][1] + gq[KB % CL_PF][1], c.gid, c.tig, b0, b1);
-    if constexpr (KB + CL_PF < NB) cl_load_g<C>(c, KB + CL_PF, gq[KB % CL_PF]);
-    const double* Ik = cl_tile<C, KB, KB>(c);
-    double h0 = 0.0, h1 = 0.0;
-    dmma(h0, h1, Ik[c.oA0], b0);
-    dmma(h0, h1, Ik[c.oA1], b1);
-    acc[KB][0] = h0; acc[KB][1] = h1;
-    cl_cvt_c_to_b(-h0, -h1, c.gid, c.tig, b0, b1);
-    cl_trail_fwd<NB, C, KB, KB + 1>(acc, c, c.oA0, b0);
-    cl_trail_fwd<NB, C, KB, KB + 1>(acc, c, c.oA1, b1);
-    cl_fwd<NB, C, KB + 1>(acc, gq, c);
+    double ikn[2] = {0.0, 0.0};
+    if (KB >= c.kb_start) {   // warp-uniform: rows above the first non-zero block of the right-hand side stay zero
+      constexpr int CL_W = cl_w<NB>();
+      double buf[2 * CL_W];
+      ClTrail<NB, C, KB, true>::template load<0, CL_W>(buf, c);
+      if constexpr (KB + 1 < NB) {
+        ikn[0] = cl_ldv(cl_tile<C, KB + 1, KB + 1>(c) + c.oA0);
+        ikn[1] = cl_ldv(cl_tile<C, KB + 1, KB + 1>(c) + c.oA1);
+      }
+      double b0, b1;
+      cl_cvt_c_to_b(acc[KB][0] + gq[KB % CL_PF][0], acc[KB][1] + gq[KB % CL_PF][1], c.gid, c.tig, b0, b1);
+      if constexpr (KB + CL_PF < NB) cl_load_g<C>(c, KB + CL_PF, gq[KB % CL_PF]);
+      double h0 = 0.0, h1 = 0.0;
+      dmma(h0, h1, ik[0], b0);
+      dmma(h0, h1, ik[1], b1);
+      acc[KB][0] = h0; acc[KB][1] = h1;
+      cl_cvt_c_to_b(-h0, -h1, c.gid, c.tig, b0, b1);
+      ClTrail<NB, C, KB, true>::template run<0>(acc, buf, c, b0, b1);
+    } else {
+      if constexpr (KB + CL_PF < NB) cl_load_g<C>(c, KB + CL_PF, gq[KB % CL_PF]);
+      if constexpr (KB + 1 < NB) {
+        ikn[0] = cl_ldv(cl_tile<C, KB + 1, KB + 1>(c) + c.oA0);
+        ikn[1] = cl_ldv(cl_tile<C, KB + 1, KB + 1>(c) + c.oA1);
+      }
+    }
+    cl_fwd<NB, C, KB + 1>(acc, gq, ikn, c);
   }
 }
 // backward, right-looking: Q[kb] = I_kb^T acc[kb]; acc[ib] -= L[kb][ib]^T Q[kb] (ib < kb)
 template <int NB, int C, int KB>
-__device__ __forceinline__ void cl_bwd(double (&acc)[NB][2], const ClCtx<C>& c) {
+__device__ __forceinline__ void cl_bwd(double (&acc)[NB][2], double (&ik)[2], const ClCtx<C>& c) {
   if constexpr (KB >= 0) {
+    constexpr int CL_W = cl_w<NB>();
+    double buf[2 * CL_W];
+    double ikn[2] = {0.0, 0.0};
+    ClTrail<NB, C, KB, false>::template load<0, CL_W>(buf, c);
+    if constexpr (KB >= 1) {
+      ikn[0] = cl_ldv(cl_tile<C, KB - 1, KB - 1>(c) + c.oT0);
+      ikn[1] = cl_ldv(cl_tile<C, KB - 1, KB - 1>(c) + c.oT1);
+    }
     double b0, b1;
     cl_cvt_c_to_b(acc[KB][0], acc[KB][1], c.gid, c.tig, b0, b1);
-    const double* Ik = cl_tile<C, KB, KB>(c);
     double q0 = 0.0, q1 = 0.0;
-    dmma(q0, q1, Ik[c.oT0], b0);
-    dmma(q0, q1, Ik[c.oT1], b1);
+    dmma(q0, q1, ik[0], b0);
+    dmma(q0, q1, ik[1], b1);
     acc[KB][0] = q0; acc[KB][1] = q1;
     cl_cvt_c_to_b(-q0, -q1, c.gid, c.tig, b0, b1);
-    cl_trail_bwd<NB, C, KB, 0>(acc, c, c.oT0, b0);
-    cl_trail_bwd<NB, C, KB, 0>(acc, c, c.oT1, b1);
-    cl_bwd<NB, C, KB - 1>(acc, c);
+    ClTrail<NB, C, KB, false>::template run<0>(acc, buf, c, b0, b1);
+    cl_bwd<NB, C, KB - 1>(acc, ikn, c);
   }
 }
 // epilogue of a column block, two row tiles at a time with every global load issued before the first use:
@@ -166,7 +269,7 @@ __device__ __forceinline__ void cl_epilogue(double (&acc)[NB][2], const ClCtx<C>
                                             double* rsw, double wS, bool need_grad, bool first_sample) {
   if constexpr (IB < NB) {
     constexpr int T = (IB + 1 < NB) ? 2 : 1;
-    double ee[T][2], gm[T][2], gs[T][2], u1[T][2], u2[T][2];
+    double ee[T][2], gg[T][2], u1[T][2], u2[T][2];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int d = 8 * (IB + t) + c.gid;
@@ -176,8 +279,7 @@ __device__ __forceinline__ void cl_epilogue(double (&acc)[NB][2], const ClCtx<C>
         const bool ok = need_grad && d < c.D && k < c.nu;
         const int r = ok ? d * c.nu + k : 0;
         ee[t][e] = ok ? __ldg(c.ep + r) : 0.0;
-        gm[t][e] = ok ? c.am[r] : 0.0;
-        gs[t][e] = ok ? c.as_[r] : 0.0;
+        gg[t][e] = ok ? c.G[d * c.ldgs + k] : 0.0;
         u1[t][e] = (ok && !first_sample) ? U1[r] : 0.0;
         u2[t][e] = (ok && !first_sample) ? U2[r] : 0.0;
       }
@@ -193,7 +295,7 @@ __device__ __forceinline__ void cl_epilogue(double (&acc)[NB][2], const ClCtx<C>
         if (d < c.D && k == c.ycol) alpha0[d] = -q;
         if (need_grad && d < c.D && k < c.nu) {
           const int r = d * c.nu + k;
-          rs += q * (gm[t][e] + gs[t][e] * ee[t][e]);
+          rs += q * gg[t][e];
           const double gb = -wS * q;
           U1[r] = u1[t][e] + gb;
           U2[r] = u2[t][e] + gb * ee[t][e];
@@ -214,12 +316,13 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 
 template <int NB, int C>
 __global__ void __launch_bounds__(CL_WARPS * 32, 1)
-wishart_loglik_cluster_kernel(const LikParams p) {
+wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const LikParams p, const int ldgs, const int box_rows) {
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(128) double sm[];
   const int D = p.D, nu = p.nu, R = D * nu, N = p.N;
-  const ClLayout L = cl_layout<C>(NB);
-  const int Dp = L.Dp, Dm = L.Dm;
+  constexpr ClLayout L = cl_layout<C>(NB);
+  constexpr int Dp = L.Dp, Dm = L.Dm, ST = L.ST;
+  constexpr int STAGE = Dm * CL_PC;   // doubles per panel stage
   double* tiles = sm;
   double* pan = sm + L.off_pan;
   double* dinv = sm + L.off_vec;
@@ -240,11 +343,14 @@ wishart_loglik_cluster_kernel(const LikParams p) {
   const int oA0 = swz(gid, tig), oA1 = swz(gid, 4 + tig);
   const int oT0 = swz(tig, gid), oT1 = swz(4 + tig, gid);
   const int oC = swz(gid, 2 * tig);
-  // per-cluster global slot: am, as (A o fmean, A o sqrt(fvar)), U1, U2 (sample sums of Gbar, Gbar o eps)
-  double* am = p.ws + (long long)cid * p.ws_stride;
-  double* as_ = am + R;
-  double* U1 = as_ + R;
+  // per-cluster global slot: G (D rows of pitch ldgs: this sample's A o (fmean + sqrt(fvar) o eps)), then U1, U2
+  // (sample sums of Gbar, Gbar o eps)
+  double* Gs = p.ws + (long long)cid * p.ws_stride;
+  double* U1 = Gs + (long long)D * ldgs;
   double* U2 = U1 + R;
+  const uint32_t pan_u32 = smem_u32(pan);
+  const uint32_t full_bar = smem_u32(sm + L.off_bar), empty_bar = full_bar + 8 * CL_MAXST;
+  uint32_t pbase = 0;   // panels this CTA has consumed so far (kernel lifetime; uniform over the CTA)
   constexpr int nbm = (NB + 1) / 2, nmac = nbm * (nbm + 1) / 2;
   const int npan = (nu + CL_PC - 1) / CL_PC;
   const int ycol = nu, ncb = nu / 8 + 1;  // column `nu` carries e_D (its solution is -alpha)
@@ -261,23 +367,28 @@ wishart_loglik_cluster_kernel(const LikParams p) {
   };
 
   for (int d = tid; d < Dp; d += blockDim.x) spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
+  if (tid == 0) {
+    for (int i = 0; i < ST; ++i) { cl_mbar_init(full_bar + 8 * i, 1); cl_mbar_init(empty_bar + 8 * i, CL_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+  }
+  // panel g (sequence number over the kernel's lifetime) into its ring stage; issued by thread 0 only
+  auto issue_panel = [&](uint32_t g, int k0) {
+    const uint32_t stage = g % ST, round = g / ST;
+    if (round > 0) cl_mbar_wait(empty_bar + 8 * stage, (round & 1u) ^ 1u);
+    cl_mbar_expect_tx(full_bar + 8 * stage, (uint32_t)(STAGE * 8));
+    for (int r0 = 0; r0 < Dm; r0 += box_rows)
+      cl_tma_load_3d(pan_u32 + (stage * STAGE + r0 * CL_PC) * 8, &tmG, full_bar + 8 * stage, k0, r0, cid);
+  };
   double glam_acc[2] = {0.0, 0.0};  // CTA 0, thread tid: d = tid and d = tid + 256
   cluster.sync();                   // every CTA of the cluster is resident before any remote access
 
   for (int n = cid; n < N; n += ncl) {
     const double* fm = p.fmean + (long long)n * p.ldf;
     const double* fv = p.fvar + (long long)n * p.ldf;
-    // ---------------- P0. per-time-step staging (split over the cluster) ----------------
-    for (int r = gtid; r < R; r += CT) {
-      const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
-      am[r] = a * fm[r];
-      as_[r] = a * sqrt(fv[r]);
-    }
     for (int d = tid; d < Dp; d += blockDim.x) yv[d] = d < D ? p.y[(long long)n * D + d] : 0.0;
     if (tid < C) badv[tid] = 0.0;
     double ve_acc = 0.0;
-    __threadfence();
-    cluster.sync();
 
     for (int s = 0; s < p.S; ++s) {
       const double* ep = p.eps + ((long long)s * N + n) * R;
@@ -294,34 +405,33 @@ wishart_loglik_cluster_kernel(const LikParams p) {
           }
         }
       }
-      // ---------------- P1. Sigma tiles = G G^T ----------------
-      double pa_[CL_PE], ps_[CL_PE], pe_[CL_PE];
-      auto panel_load = [&](int pi) {
-        const int k0 = CL_PC * pi;
+      // ---------------- P0. G = A o (fmean + sqrt(fvar) o eps) of this sample into the cluster's slot ----------------
+      for (int base = gtid; base < R; base += 4 * CT) {   // four elements per thread in flight (coalesced over the cluster)
+        double a4[4], f4[4], v4[4], e4[4];
 #pragma unroll
-        for (int i = 0; i < CL_PE; ++i) {
-          const int e = tid + i * CL_WARPS * 32;
-          const int d = e / CL_PC, k = k0 + (e % CL_PC);
-          const bool ok = d < D && k < nu;
-          const int r = ok ? d * nu + k : 0;
-          pa_[i] = ok ? am[r] : 0.0;
-          ps_[i] = ok ? as_[r] : 0.0;
-          pe_[i] = ok ? __ldg(ep + r) : 0.0;
+        for (int u = 0; u < 4; ++u) {
+          const int r = base + u * CT;
+          if (r < R) {
+            a4[u] = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
+            f4[u] = fm[r];
+            v4[u] = fv[r];
+            e4[u] = __ldg(ep + r);
+          }
         }
-      };
-      auto panel_store = [&](int buf) {
-        double* dst = pan + buf * Dm * CL_PC;
 #pragma unroll
-        for (int i = 0; i < CL_PE; ++i) {
-          const int e = tid + i * CL_WARPS * 32;
-          if (e / CL_PC < D) dst[e] = pa_[i] + ps_[i] * pe_[i];
+        for (int u = 0; u < 4; ++u) {
+          const int r = base + u * CT;
+          if (r < R) {
+            const int d = r / nu, k = r - d * nu;
+            const double gm = a4[u] * f4[u], gs = a4[u] * sqrt(v4[u]);
+            Gs[d * ldgs + k] = gm + gs * e4[u];
+          }
         }
-      };
-      // panel rows >= D are zero (the buffers double as row-sum scratch in P4)
-      for (int e = tid; e < 2 * Dm * CL_PC; e += blockDim.x) {
-        const int row = (e % (Dm * CL_PC)) / CL_PC;
-        if (row >= D) pan[e] = 0.0;
       }
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");   // generic writes (G, the row-sum scratch) before the TMA reads / writes
+      cluster.sync();
+      // ---------------- P1. Sigma tiles = G G^T ----------------
       for (int mbase = 0; mbase < nmac; mbase += CW * CL_MQ) {
         int Iq[CL_MQ], Jq[CL_MQ];
         bool on[CL_MQ];
@@ -340,13 +450,15 @@ wishart_loglik_cluster_kernel(const LikParams p) {
 #pragma unroll
             for (int v = 0; v < 2; ++v) acc[q][u][v][0] = acc[q][u][v][1] = 0.0;
         }
-        __syncthreads();  // previous users of the panel buffers are done
-        panel_load(0);
-        panel_store(0);
-        __syncthreads();
+        if (tid == 0) {
+          for (int j = 0; j < ST - 1 && j < npan; ++j) issue_panel(pbase + j, CL_PC * j);
+        }
         for (int pi = 0; pi < npan; ++pi) {
-          if (pi + 1 < npan) panel_load(pi + 1);
-          const double* P = pan + (pi & 1) * Dm * CL_PC;
+          const uint32_t g = pbase + pi, stage = g % ST;
+          cl_mbar_wait(full_bar + 8 * stage, (g / ST) & 1u);
+          // refill the stage every warp released one k-step ago
+          if (tid == 0 && pi + ST - 1 < npan) issue_panel(g + ST - 1, CL_PC * (pi + ST - 1));
+          const double* P = pan + stage * STAGE;
 #pragma unroll
           for (int q = 0; q < CL_MQ; ++q) {
             if (!on[q]) continue;
@@ -358,9 +470,10 @@ wishart_loglik_cluster_kernel(const LikParams p) {
             dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
             dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
           }
-          if (pi + 1 < npan) panel_store((pi + 1) & 1);
-          __syncthreads();
+          __syncwarp();
+          if (lane == 0) cl_mbar_arrive(empty_bar + 8 * stage);
         }
+        pbase += (uint32_t)npan;
         // + diag(softplus(lam)), bordered y row, identity padding; store the lower tiles into their owners
 #pragma unroll
         for (int q = 0; q < CL_MQ; ++q) {
@@ -396,13 +509,14 @@ wishart_loglik_cluster_kernel(const LikParams p) {
         // (a) column jb of this CTA's block rows: S[ib][jb] -= sum_{kb < jb} L[ib][kb] L[jb][kb]^T
         {
           const int lr0 = jb > rank ? (jb - rank + C - 1) / C : 0;
-          double c[SL][2];
+          double c[SL][2], c2[SL][2];   // two partial sums (even / odd kb): half the dependent DMMA chain
           int lrs[SL];
           bool on[SL];
 #pragma unroll
           for (int t = 0; t < SL; ++t) {
             lrs[t] = lr0 + warp + t * CL_WARPS;
             on[t] = lrs[t] * C + rank < NB;
+            c2[t][0] = c2[t][1] = 0.0;
             if (on[t]) {
               const double2 v = *reinterpret_cast<const double2*>(tile_own(lrs[t], jb) + oC);
               c[t][0] = v.x; c[t][1] = v.y;
@@ -410,19 +524,38 @@ wishart_loglik_cluster_kernel(const LikParams p) {
           }
           if (on[0]) {
             const double* Tj = tile_any(jb, 0);   // block row jb is contiguous in its owner: tile (jb, kb) = Tj + 64 kb
-#pragma unroll 4
-            for (int kb = 0; kb < jb; ++kb) {
+            int kb = 0;
+#pragma unroll 2
+            for (; kb + 1 < jb; kb += 2) {
+              const double nb0 = -Tj[kb * 64 + oA0], nb1 = -Tj[kb * 64 + oA1];
+              const double nd0 = -Tj[kb * 64 + 64 + oA0], nd1 = -Tj[kb * 64 + 64 + oA1];
+#pragma unroll
+              for (int t = 0; t < SL; ++t) {
+                if (on[t]) {
+                  const double* t0 = tile_own(lrs[t], kb);
+                  const double x0 = t0[oA0], x1 = t0[oA1], y0 = t0[64 + oA0], y1 = t0[64 + oA1];
+                  dmma(c[t][0], c[t][1], x0, nb0);
+                  dmma(c2[t][0], c2[t][1], y0, nd0);
+                  dmma(c[t][0], c[t][1], x1, nb1);
+                  dmma(c2[t][0], c2[t][1], y1, nd1);
+                }
+              }
+            }
+            if (kb < jb) {
               const double nb0 = -Tj[kb * 64 + oA0], nb1 = -Tj[kb * 64 + oA1];
 #pragma unroll
-              for (int t = 0; t < SL; ++t)
-                if (on[t]) dmma(c[t][0], c[t][1], tile_own(lrs[t], kb)[oA0], nb0);
-#pragma unroll
-              for (int t = 0; t < SL; ++t)
-                if (on[t]) dmma(c[t][0], c[t][1], tile_own(lrs[t], kb)[oA1], nb1);
+              for (int t = 0; t < SL; ++t) {
+                if (on[t]) {
+                  const double* t0 = tile_own(lrs[t], kb);
+                  dmma(c[t][0], c[t][1], t0[oA0], nb0);
+                  dmma(c[t][0], c[t][1], t0[oA1], nb1);
+                }
+              }
             }
 #pragma unroll
             for (int t = 0; t < SL; ++t)
-              if (on[t]) *reinterpret_cast<double2*>(tile_own(lrs[t], jb) + oC) = make_double2(c[t][0], c[t][1]);
+              if (on[t])
+                *reinterpret_cast<double2*>(tile_own(lrs[t], jb) + oC) = make_double2(c[t][0] + c2[t][0], c[t][1] + c2[t][1]);
           }
         }
         __syncthreads();
@@ -479,8 +612,9 @@ wishart_loglik_cluster_kernel(const LikParams p) {
         ClCtx<C> c;
 #pragma unroll
         for (int r = 0; r < C; ++r) c.rb[r] = cluster.map_shared_rank(tiles, r);
-        c.am = am; c.as_ = as_; c.ep = ep; c.D = D; c.nu = nu; c.colC = 8 * cb + 2 * tig;
+        c.G = Gs; c.ep = ep; c.D = D; c.nu = nu; c.ldgs = ldgs; c.colC = 8 * cb + 2 * tig;
         c.ycol = ycol; c.gid = gid; c.tig = tig; c.oA0 = oA0; c.oA1 = oA1; c.oT0 = oT0; c.oT1 = oT1;
+        c.kb_start = 8 * cb >= nu ? yb : 0;   // the block past the last column of G holds only e_D (row D = block yb)
         double acc[NB][2], gq[CL_PF][2];
 #pragma unroll
         for (int ib = 0; ib < NB; ++ib) acc[ib][0] = acc[ib][1] = 0.0;
@@ -489,7 +623,10 @@ wishart_loglik_cluster_kernel(const LikParams p) {
           gq[t][0] = gq[t][1] = 0.0;
           if (t < NB) cl_load_g<C>(c, t, gq[t]);
         }
-        cl_fwd<NB, C, 0>(acc, gq, c);
+        double ik[2];
+        ik[0] = cl_ldv(cl_tile<C, 0, 0>(c) + oA0);
+        ik[1] = cl_ldv(cl_tile<C, 0, 0>(c) + oA1);
+        cl_fwd<NB, C, 0>(acc, gq, ik, c);
         // row D of H is -alpha^T G: negate it so that the back substitution folds in - alpha (alpha^T G)
         // (the e_D column keeps its sign: its solution is column D of L^-T = (-alpha; 1))
 #pragma unroll
@@ -499,7 +636,9 @@ wishart_loglik_cluster_kernel(const LikParams p) {
             if (c.colC + 1 != ycol) acc[ib][1] = -acc[ib][1];
           }
         }
-        cl_bwd<NB, C, NB - 1>(acc, c);
+        ik[0] = cl_ldv(cl_tile<C, NB - 1, NB - 1>(c) + oT0);
+        ik[1] = cl_ldv(cl_tile<C, NB - 1, NB - 1>(c) + oT1);
+        cl_bwd<NB, C, NB - 1>(acc, ik, c);
         cl_epilogue<NB, C, 0>(acc, c, U1, U2, alpha0, rsw, wS, p.need_grad != 0, s == 0);
       }
       cluster.sync();
@@ -555,7 +694,7 @@ wishart_loglik_cluster_kernel(const LikParams p) {
       p.info[n] = b;
     }
     __threadfence();
-    cluster.sync();   // the slot (am, as, U1, U2) and the flags are re-used by the next time step
+    cluster.sync();   // the slot (G, U1, U2) and the flags are re-used by the next time step
   }
   if (p.need_grad && rank == 0) {
 #pragma unroll
@@ -567,34 +706,63 @@ wishart_loglik_cluster_kernel(const LikParams p) {
 }
 
 static constexpr long long kSmemLimitC = 227 * 1024;
-static constexpr int kClusterC = 4;
 
-// row-block capacities instantiated (the padded system has 8 NB rows; rows > D are identity)
+// Row-block capacities instantiated (the padded system has 8 NB rows; rows > D are identity) and the cluster size of
+// each: pairs while half of the tiles fit one SM (D <= 303: half of the operand reads stay local and all 148 SMs are used;
+// 24.8 ms against 34.9 ms for clusters of four at D = 256, N = 296, S = 8), clusters of four above (132 SMs can host them).
+#ifdef FCEST_CL_DEV   // development builds: two instantiations only (each takes ~50 s to compile)
+static const int kCaps[] = {34, 51};
+#else
+static const int kCaps[] = {30, 34, 38, 42, 46, 51};
+#endif
 static int cluster_capacity(int D) {
   const int need = D / 8 + 1;
-  const int caps[] = {30, 34, 38, 42, 46, 51};
-  for (int c : caps) if (need <= c) return c;
+  for (int c : kCaps) if (need <= c) return c;
   return 0;
 }
+static int cluster_size(int NB) { return NB <= 38 ? 2 : 4; }
 
 bool loglik_cluster_supported(int D, int nu) {
   if (D < 8 || nu < 1 || nu > 407) return false;
   const int NB = cluster_capacity(D);
   if (!NB) return false;
-  return (long long)cl_layout<kClusterC>(NB).total * 8 + 64 <= kSmemLimitC;
+  const long long total = cluster_size(NB) == 2 ? cl_layout<2>(NB).total : cl_layout<4>(NB).total;
+  return total * 8 + 64 <= kSmemLimitC;
+}
+
+// per-cluster slot: G (D rows of pitch ldgs = nu rounded up to 4: 32-byte aligned rows for the tensor map), U1, U2
+static long long cluster_slot_doubles(int D, int nu) {
+  const long long ldgs = (nu + 3) & ~3;
+  return ((long long)D * ldgs + 2LL * D * nu + 1) & ~1LL;
 }
 
 long long loglik_cluster_scratch_bytes(int D, int nu) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  return (long long)sizeof(double) * 4LL * D * nu * (sms / kClusterC);
+  return (long long)sizeof(double) * cluster_slot_doubles(D, nu) * (sms / 2);   // clusters of two at most
 }
 
-template <int NB>
+typedef CUresult (*ClEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static ClEncodeTiledFn cl_encode_fn() {
+  static ClEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (ClEncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+template <int NB, int C>
 static int launch_cluster_nb(const LikParams& p, cudaStream_t stream, int* part_rows) {
-  constexpr int C = kClusterC;
-  const long long smem = (long long)cl_layout<C>(NB).total * 8;
+  constexpr ClLayout L = cl_layout<C>(NB);
+  const long long smem = (long long)L.total * 8;
   auto kern = wishart_loglik_cluster_kernel<NB, C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -620,7 +788,22 @@ static int launch_cluster_nb(const LikParams& p, cudaStream_t stream, int* part_
   if (ncl > sms / C) ncl = sms / C;
   if (ncl > p.N) ncl = p.N;
   cfg.gridDim = dim3((unsigned)(ncl * C), 1, 1);
-  e = cudaLaunchKernelEx(&cfg, kern, p);
+  // tensor map over the G slots of all clusters: (nu columns, D rows, ncl slots); a box is 4 columns x box_rows rows of
+  // one slot, rows >= D and columns >= nu are zero-filled by the copy engine
+  ClEncodeTiledFn enc = cl_encode_fn();
+  if (!enc) return FCEST_ERR_UNSUPPORTED;
+  const int ldgs = (p.nu + 3) & ~3;
+  const int box_rows = L.Dm > 256 ? L.Dm / 2 : L.Dm;
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)p.nu, (cuuint64_t)p.D, (cuuint64_t)ncl};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldgs * 8, (cuuint64_t)p.ws_stride * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)CL_PC, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)p.ws, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return FCEST_ERR_ARGUMENT;
+  e = cudaLaunchKernelEx(&cfg, kern, tm, p, ldgs, box_rows);
   if (e != cudaSuccess) return (int)e;
   *part_rows = ncl;
   return 0;
@@ -629,14 +812,16 @@ static int launch_cluster_nb(const LikParams& p, cudaStream_t stream, int* part_
 int launch_loglik_cluster(LikParams p, cudaStream_t stream, int* part_rows) {
   if (!loglik_cluster_supported(p.D, p.nu)) return -1;
   if (p.ws == nullptr) return FCEST_ERR_ARGUMENT;
-  p.ws_stride = 4LL * p.D * p.nu;
+  p.ws_stride = cluster_slot_doubles(p.D, p.nu);
   switch (cluster_capacity(p.D)) {
-    case 30: return launch_cluster_nb<30>(p, stream, part_rows);
-    case 34: return launch_cluster_nb<34>(p, stream, part_rows);
-    case 38: return launch_cluster_nb<38>(p, stream, part_rows);
-    case 42: return launch_cluster_nb<42>(p, stream, part_rows);
-    case 46: return launch_cluster_nb<46>(p, stream, part_rows);
-    case 51: return launch_cluster_nb<51>(p, stream, part_rows);
+    case 34: return launch_cluster_nb<34, 2>(p, stream, part_rows);
+    case 51: return launch_cluster_nb<51, 4>(p, stream, part_rows);
+#ifndef FCEST_CL_DEV
+    case 30: return launch_cluster_nb<30, 2>(p, stream, part_rows);
+    case 38: return launch_cluster_nb<38, 2>(p, stream, part_rows);
+    case 42: return launch_cluster_nb<42, 4>(p, stream, part_rows);
+    case 46: return launch_cluster_nb<46, 4>(p, stream, part_rows);
+#endif
     default: return -1;
   }
 }

@@ -124,8 +124,9 @@ def test_warp_and_cta_kernels_agree(cuda):
         assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max(), k
 
 
-# D above the shared-memory tile store (208 <= D <= 400; the reference takes any D, likelihoods.py:185)
-@pytest.mark.parametrize("D", [256, 320, 400])
+# D above the single-SM tile store (208 <= D <= 400; the reference takes any D, likelihoods.py:185): cluster-tiled kernel
+# (likelihood_cluster.cu), one size per instantiated row-block capacity (30 / 34 / 38: CTA pairs, 42 / 46 / 51: clusters of 4)
+@pytest.mark.parametrize("D", [232, 256, 300, 320, 360, 400])
 def test_loglik_large_D(cuda, D):
     _check(N=2, D=D, S=2, seed=D)
 
@@ -168,7 +169,7 @@ def test_kernels_are_run_to_run_deterministic(cuda):
     give bit-identical outputs -- the race evidence available here (compute-sanitizer is closed on this pool)."""
     from fcest_b200 import ops
     from fcest_b200.models import SlidingWindows
-    for D, N, S in ((50, 40, 8), (72, 6, 3)):
+    for D, N, S in ((50, 40, 8), (72, 6, 3), (256, 3, 2)):
         fmean, fvar, y, A, lam, eps = _inputs(N, D, S, 3)
         args = (ops.as_pitched(fmean.cuda()), ops.as_pitched(fvar.cuda()), eps.cuda(), y.cuda(), A.cuda(), lam.cuda())
         ref = ops.wishart_loglik(*args)
