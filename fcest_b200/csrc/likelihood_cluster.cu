@@ -406,10 +406,11 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
         }
       }
       // ---------------- P0. G = A o (fmean + sqrt(fvar) o eps) of this sample into the cluster's slot ----------------
-      for (int base = gtid; base < R; base += 4 * CT) {   // four elements per thread in flight (coalesced over the cluster)
-        double a4[4], f4[4], v4[4], e4[4];
+      constexpr int GF = 8;
+      for (int base = gtid; base < R; base += GF * CT) {   // GF elements per thread in flight (coalesced over the cluster)
+        double a4[GF], f4[GF], v4[GF], e4[GF];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < GF; ++u) {
           const int r = base + u * CT;
           if (r < R) {
             a4[u] = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
@@ -419,11 +420,12 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < GF; ++u) {
           const int r = base + u * CT;
           if (r < R) {
             const int d = r / nu, k = r - d * nu;
-            const double gm = a4[u] * f4[u], gs = a4[u] * sqrt(v4[u]);
+            const double sd = v4[u] > 0.0 ? v4[u] * rsqrt(v4[u]) : 0.0;   // inline (sqrt() keeps a slow-path call: spills)
+            const double gm = a4[u] * f4[u], gs = a4[u] * sd;
             Gs[d * ldgs + k] = gm + gs * e4[u];
           }
         }

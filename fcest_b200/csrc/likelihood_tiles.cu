@@ -7,10 +7,13 @@
 // Why: the L2-scratch variant in likelihood.cu fetches every DMMA operand fragment from global memory and is
 // L2-bandwidth bound (3.9 TFLOP/s at D = 200).  Here every operand of the O(D^3) phases comes from shared
 // memory or registers:
-//   P0  per time step: am = A o fmean, as = A o sqrt(fvar) into a per-CTA global slot (L2 resident), shared by
-//       the S samples the CTA walks through.
-//   P1  Sigma = G G^T: output-stationary 16 x 16 macro tiles in registers (6 per warp and pass), G streamed
-//       through a double-buffered 8-column shared-memory panel built on the fly from am, as and eps.
+//   P0  (separate streaming kernel, per chunk of time steps) G = A o (fmean + sqrt(fvar) o eps) for all samples of the
+//       chunk, written once at HBM speed (`wishart_g_fill_kernel`); filling G inside the persistent kernel cost 30 % of
+//       its time (148 CTAs x 1.6 MB of per-CTA state thrash the L2 and the loads are latency-exposed).
+//   P1  Sigma = G G^T: output-stationary 16 x 16 macro tiles in registers (6 per warp and pass); G arrives as
+//       4-column panels (one DMMA k-step; dense 32-byte rows are conflict-free for the fragment reads) through a ring
+//       of six TMA tensor-map copies (`cp.async.bulk.tensor.3d`, SASS UTMALDG; rows >= D zero-filled by the copy
+//       engine) with full / empty mbarriers: no registers and no block barrier in the k loop.
 //   P2  left-looking blocked Cholesky on the shared-memory tiles (bordered y row, unit pivot); diagonal tiles
 //       factored + inverted in registers (lik_tiles.cuh); three block barriers per block column.
 //   P4  per 8-column block of G (one warp each, no block barrier): right-looking block forward substitution
@@ -19,6 +22,7 @@
 //       e_D whose solution is -alpha.  Per-sample cotangents accumulate in the CTA's global slot (U1, U2).
 //   P5  lam_bar, ve; after the last sample one coalesced pass turns U1, U2 into mu_bar, v_bar, A_bar partials.
 // Deterministic: every accumulation has a fixed owner and order.
+#include <cuda.h>
 #include <math.h>
 
 #include "chol_tiles.cuh"
@@ -31,26 +35,59 @@ namespace fcest {
 
 constexpr int LT_WARPS = 8;
 constexpr int LT_MQ = 6;     // macro tiles per warp and SYRK pass
-constexpr int LT_PP = 12;    // pitch of the 8-column G panel (4 mod 8: conflict-free fragment reads)
+constexpr int LT_PC = 4;     // columns of a G panel = one DMMA k-step (dense 32-byte rows: fragment reads are contiguous)
+constexpr int LT_ST = 6;     // panel stages in the TMA ring
 
 struct TilesLayout {
   int NB, Dp, Dm, NT;
-  int off_pan, off_vec, total;  // doubles
+  int off_pan, off_vec, off_bar, total;  // doubles
 };
 
 // NB = row-block capacity of the instantiation (>= D / 8 + 1; rows > D are identity padding)
-__host__ __device__ inline TilesLayout lt_layout(int NB) {
-  TilesLayout L;
+__host__ __device__ constexpr TilesLayout lt_layout(int NB) {
+  TilesLayout L = {};
   L.NB = NB;
   L.Dp = 8 * L.NB;
   L.Dm = (L.Dp + 15) / 16 * 16;
   L.NT = L.NB * (L.NB + 1) / 2;
   L.off_pan = L.NT * 64;
-  int pan = 2 * L.Dm * LT_PP;                       // two panel buffers (P1); reused as 8 x Dp row-sum partials (P4)
+  int pan = LT_ST * L.Dm * LT_PC;                   // panel ring (P1); reused as 8 x Dp row-sum partials (P4)
   if (pan < LT_WARPS * L.Dp) pan = LT_WARPS * L.Dp;
   L.off_vec = L.off_pan + pan;
-  L.total = L.off_vec + 4 * L.Dp + 16;              // dinv, yv, spl, alpha, misc
+  L.off_bar = L.off_vec + 4 * L.Dp + 16;            // dinv, yv, spl, alpha, misc
+  L.total = L.off_bar + 2 * LT_ST;                  // full / empty mbarriers
   return L;
+}
+
+__device__ __forceinline__ void lt_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void lt_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lt_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void lt_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA tensor-map copy of one panel (4 columns x Dm rows of this CTA's G slot) global -> shared (SASS UTMALDG)
+__device__ __forceinline__ void lt_tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 
 // accumulator-layout tile (c0 = [gid][2 tig], c1 = [gid][2 tig + 1]) -> B-operand fragments
@@ -66,8 +103,8 @@ __device__ __forceinline__ void cvt_c_to_b(double c0, double c1, int gid, int ti
 
 // Context of one column-block solve (P4); passed by reference through the unrolled step templates.
 struct LtCtx {
-  const double* tiles; const double* am; const double* as_; const double* ep;
-  int D, nu, colC, ycol, gid, tig, oA0, oA1, oT0, oT1;
+  const double* tiles; const double* G; const double* ep;   // G slot (row pitch ldgs), noise of this sample
+  int D, nu, ldgs, colC, ycol, gid, tig, oA0, oA1, oT0, oT1;
 };
 
 // G tile (ib, cb) in accumulator layout; column ycol carries e_D
@@ -77,7 +114,7 @@ __device__ __forceinline__ void lt_load_g(const LtCtx& c, int ib, double (&g)[2]
   for (int e = 0; e < 2; ++e) {
     const int k = c.colC + e;
     double v = 0.0;
-    if (d < c.D && k < c.nu) { const int r = d * c.nu + k; v = c.am[r] + c.as_[r] * __ldg(c.ep + r); }
+    if (d < c.D && k < c.nu) v = c.G[d * c.ldgs + k];
     else if (d == c.D && k == c.ycol) v = 1.0;
     g[e] = v;
   }
@@ -142,7 +179,7 @@ __device__ __forceinline__ void lt_epilogue(double (&acc)[NB][2], const LtCtx& c
                                             double* rsw, double wS, bool need_grad, bool first_sample) {
   if constexpr (IB < NB) {
     constexpr int T = (IB + 1 < NB) ? 2 : 1;
-    double ee[T][2], gm[T][2], gs[T][2], u1[T][2], u2[T][2];
+    double ee[T][2], gg[T][2], u1[T][2], u2[T][2];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int d = 8 * (IB + t) + c.gid;
@@ -152,8 +189,7 @@ __device__ __forceinline__ void lt_epilogue(double (&acc)[NB][2], const LtCtx& c
         const bool ok = need_grad && d < c.D && k < c.nu;
         const int r = ok ? d * c.nu + k : 0;
         ee[t][e] = ok ? __ldg(c.ep + r) : 0.0;
-        gm[t][e] = ok ? c.am[r] : 0.0;
-        gs[t][e] = ok ? c.as_[r] : 0.0;
+        gg[t][e] = ok ? c.G[d * c.ldgs + k] : 0.0;
         u1[t][e] = (ok && !first_sample) ? U1[r] : 0.0;
         u2[t][e] = (ok && !first_sample) ? U2[r] : 0.0;
       }
@@ -169,7 +205,7 @@ __device__ __forceinline__ void lt_epilogue(double (&acc)[NB][2], const LtCtx& c
         if (d < c.D && k == c.ycol) alpha[d] = -q;
         if (need_grad && d < c.D && k < c.nu) {
           const int r = d * c.nu + k;
-          rs += q * (gm[t][e] + gs[t][e] * ee[t][e]);
+          rs += q * gg[t][e];
           const double gb = -wS * q;
           U1[r] = u1[t][e] + gb;
           U2[r] = u2[t][e] + gb * ee[t][e];
@@ -185,11 +221,13 @@ __device__ __forceinline__ void lt_epilogue(double (&acc)[NB][2], const LtCtx& c
 
 template <int NB>
 __global__ void __launch_bounds__(LT_WARPS * 32, 1)
-wishart_loglik_tiles_kernel(const LikParams p) {
-  extern __shared__ __align__(16) double sm[];
+wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikParams p, const int ldgs, const double* Gc,
+                            const int n0, const int nc) {
+  extern __shared__ __align__(128) double sm[];
   const int D = p.D, nu = p.nu, R = D * nu, N = p.N;
-  const TilesLayout L = lt_layout(NB);
-  const int Dp = L.Dp, Dm = L.Dm;
+  constexpr TilesLayout L = lt_layout(NB);
+  constexpr int Dp = L.Dp, Dm = L.Dm;
+  constexpr int STAGE = Dm * LT_PC;   // doubles per panel stage
   double* tiles = sm;
   double* pan = sm + L.off_pan;
   double* dinv = sm + L.off_vec;
@@ -205,30 +243,37 @@ wishart_loglik_tiles_kernel(const LikParams p) {
   const int oA0 = swz(gid, tig), oA1 = swz(gid, 4 + tig);
   const int oT0 = swz(tig, gid), oT1 = swz(4 + tig, gid);
   const int oC = swz(gid, 2 * tig);
-  // per-CTA global slot: am, as (A o fmean, A o sqrt(fvar)), U1, U2 (sample sums of Gbar, Gbar o eps)
-  double* am = p.ws + (long long)blockIdx.x * p.ws_stride;
-  double* as_ = am + R;
-  double* U1 = as_ + R;
+  // per-CTA global slot: U1, U2 (sample sums of Gbar, Gbar o eps); Gc: G of the chunk's time steps [n0, n0 + nc),
+  // (S, nc, D) rows of pitch ldgs, filled by wishart_g_fill_kernel
+  double* U1 = p.ws + (long long)blockIdx.x * p.ws_stride;
   double* U2 = U1 + R;
   const int nbm = (NB + 1) / 2, nmac = nbm * (nbm + 1) / 2;
-  const int npan = (nu + 7) / 8;
+  const int npan = (nu + LT_PC - 1) / LT_PC;
+  const uint32_t pan_u32 = smem_u32(pan);
+  const uint32_t full_bar = smem_u32(sm + L.off_bar), empty_bar = full_bar + 8 * LT_ST;
+  uint32_t pbase = 0;   // panels consumed so far (kernel lifetime; uniform over the CTA)
+  if (tid == 0) {
+    for (int i = 0; i < LT_ST; ++i) { lt_mbar_init(full_bar + 8 * i, 1); lt_mbar_init(empty_bar + 8 * i, LT_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+  }
+  // panel g (sequence number over the kernel's lifetime) into its ring stage; issued by thread 0 only
+  auto issue_panel = [&](uint32_t g, int k0, int z) {
+    const uint32_t stage = g % LT_ST, round = g / LT_ST;
+    if (round > 0) lt_mbar_wait(empty_bar + 8 * stage, (round & 1u) ^ 1u);
+    lt_mbar_expect_tx(full_bar + 8 * stage, (uint32_t)(STAGE * 8));
+    lt_tma_load_3d(pan_u32 + stage * STAGE * 8, &tmG, full_bar + 8 * stage, k0, 0, z);
+  };
   const int ycol = nu, ncb = nu / 8 + 1;  // column `nu` carries e_D (its solution is -alpha)
   const bool vec = (nu & 1) == 0;
 
-  for (int e = tid; e < 2 * Dm * LT_PP; e += blockDim.x) pan[e] = 0.0;  // panel rows >= D stay zero
   for (int d = tid; d < Dp; d += blockDim.x) spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
   double glam_acc = 0.0;  // thread d < D (blockDim = 256 >= D)
 
-  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+  for (int n = n0 + blockIdx.x; n < n0 + nc; n += gridDim.x) {
     const double* fm = p.fmean + (long long)n * p.ldf;
     const double* fv = p.fvar + (long long)n * p.ldf;
     __syncthreads();
-    // ---------------- P0. per-time-step staging ----------------
-    for (int r = tid; r < R; r += blockDim.x) {
-      const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
-      am[r] = a * fm[r];
-      as_[r] = a * sqrt(fv[r]);
-    }
     for (int d = tid; d < Dp; d += blockDim.x) yv[d] = d < D ? p.y[(long long)n * D + d] : 0.0;
     if (tid == 0) bad_s = 0;
     double ve_acc = 0.0;
@@ -236,33 +281,11 @@ wishart_loglik_tiles_kernel(const LikParams p) {
 
     for (int s = 0; s < p.S; ++s) {
       const double* ep = p.eps + ((long long)s * N + n) * R;
+      const int zs = s * nc + (n - n0);                       // this problem's slab of the chunk's G
+      const double* Gs = Gc + (long long)zs * D * ldgs;
+      asm volatile("fence.proxy.async;" ::: "memory");        // generic writes to the ring (row-sum scratch) before the TMA writes
+      __syncthreads();
       // ---------------- P1. Sigma tiles = G G^T ----------------
-      // panel = 8 columns of G; its raw ingredients are loaded into registers before the DMMAs of the current
-      // panel and combined / stored to the other buffer after them (D * 8 / 256 <= 7 elements per thread)
-      constexpr int PE = 7;
-      double pa_[PE], ps_[PE], pe_[PE];
-      auto panel_load = [&](int pi) {
-        const int k0 = 8 * pi;
-#pragma unroll
-        for (int i = 0; i < PE; ++i) {
-          const int e = tid + i * LT_WARPS * 32;
-          const int d = e >> 3, k = k0 + (e & 7);
-          const bool ok = d < D && k < nu;
-          const int r = ok ? d * nu + k : 0;
-          pa_[i] = ok ? am[r] : 0.0;
-          ps_[i] = ok ? as_[r] : 0.0;
-          pe_[i] = ok ? __ldg(ep + r) : 0.0;
-        }
-      };
-      auto panel_store = [&](int buf) {
-        double* dst = pan + buf * Dm * LT_PP;
-#pragma unroll
-        for (int i = 0; i < PE; ++i) {
-          const int e = tid + i * LT_WARPS * 32;
-          const int d = e >> 3;
-          if (d < D) dst[d * LT_PP + (e & 7)] = pa_[i] + ps_[i] * pe_[i];
-        }
-      };
       for (int mbase = 0; mbase < nmac; mbase += LT_WARPS * LT_MQ) {
         int Iq[LT_MQ], Jq[LT_MQ];
         bool on[LT_MQ];
@@ -281,30 +304,30 @@ wishart_loglik_tiles_kernel(const LikParams p) {
 #pragma unroll
             for (int v = 0; v < 2; ++v) acc[q][u][v][0] = acc[q][u][v][1] = 0.0;
         }
-        __syncthreads();  // previous users of the panel buffers are done
-        panel_load(0);
-        panel_store(0);
-        __syncthreads();
+        if (tid == 0) {
+          for (int j = 0; j < LT_ST - 1 && j < npan; ++j) issue_panel(pbase + j, LT_PC * j, zs);
+        }
         for (int pi = 0; pi < npan; ++pi) {
-          if (pi + 1 < npan) panel_load(pi + 1);
-          const double* P = pan + (pi & 1) * Dm * LT_PP;
+          const uint32_t g = pbase + pi, stage = g % LT_ST;
+          lt_mbar_wait(full_bar + 8 * stage, (g / LT_ST) & 1u);
+          // refill the stage every warp released one k-step ago
+          if (tid == 0 && pi + LT_ST - 1 < npan) issue_panel(g + LT_ST - 1, LT_PC * (pi + LT_ST - 1), zs);
+          const double* P = pan + stage * STAGE;
 #pragma unroll
           for (int q = 0; q < LT_MQ; ++q) {
             if (!on[q]) continue;
-            const double* pa = P + (16 * Iq[q] + gid) * LT_PP + tig;
-            const double* pb = P + (16 * Jq[q] + gid) * LT_PP + tig;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const double a0 = pa[4 * h], a1 = pa[8 * LT_PP + 4 * h], b0 = pb[4 * h], b1 = pb[8 * LT_PP + 4 * h];
-              dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
-              dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
-              dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
-              dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
-            }
+            const double* pa = P + (16 * Iq[q] + gid) * LT_PC + tig;
+            const double* pb = P + (16 * Jq[q] + gid) * LT_PC + tig;
+            const double a0 = pa[0], a1 = pa[8 * LT_PC], b0 = pb[0], b1 = pb[8 * LT_PC];
+            dmma(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+            dmma(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+            dmma(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+            dmma(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
           }
-          if (pi + 1 < npan) panel_store((pi + 1) & 1);
-          __syncthreads();
+          __syncwarp();
+          if (lane == 0) lt_mbar_arrive(empty_bar + 8 * stage);
         }
+        pbase += (uint32_t)npan;
         // + diag(softplus(lam)), bordered y row, identity padding; store the lower tiles
 #pragma unroll
         for (int q = 0; q < LT_MQ; ++q) {
@@ -400,7 +423,7 @@ wishart_loglik_tiles_kernel(const LikParams p) {
       const int cb_first = p.need_grad ? warp : (warp == 0 ? ncb - 1 : ncb);
       for (int cb = cb_first; cb < ncb; cb += LT_WARPS) {
         LtCtx c;
-        c.tiles = tiles; c.am = am; c.as_ = as_; c.ep = ep; c.D = D; c.nu = nu; c.colC = 8 * cb + 2 * tig;
+        c.tiles = tiles; c.G = Gs; c.ep = ep; c.D = D; c.nu = nu; c.ldgs = ldgs; c.colC = 8 * cb + 2 * tig;
         c.ycol = ycol; c.gid = gid; c.tig = tig; c.oA0 = oA0; c.oA1 = oA1; c.oT0 = oT0; c.oT1 = oT1;
         double acc[NB][2], gq[LT_PF][2];
 #pragma unroll
@@ -443,7 +466,7 @@ wishart_loglik_tiles_kernel(const LikParams p) {
 
     // mu_bar = a U1, v_bar = a U2 / (2 sd), A_bar partial (per CTA) += fm U1 + sd U2
     if (p.need_grad) {
-      const bool first = (n == (int)blockIdx.x);
+      const bool first = (n == (int)blockIdx.x);   // chunk 0, first time step of this CTA
       for (int r = tid; r < R; r += blockDim.x) {
         const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
         const double f = fm[r], v = fv[r], rsq = rsqrt(v), sd = v * rsq;
@@ -459,7 +482,10 @@ wishart_loglik_tiles_kernel(const LikParams p) {
       p.info[n] = bad_s;
     }
   }
-  if (p.need_grad && tid < D) p.glam_part[(long long)blockIdx.x * D + tid] = glam_acc;
+  if (p.need_grad && tid < D) {   // per-CTA partial, accumulated over the chunks in launch order
+    const long long o = (long long)blockIdx.x * D + tid;
+    p.glam_part[o] = (n0 == 0 ? 0.0 : p.glam_part[o]) + glam_acc;
+  }
 }
 
 static constexpr long long kSmemLimitT = 227 * 1024;
@@ -486,39 +512,111 @@ static int tiles_grid(int N) {
   return N < sms ? N : sms;
 }
 
-long long loglik_tiles_scratch_bytes(int D, int nu) {
+// Scratch layout: [U1, U2 slots: 2 R doubles per CTA][G of one chunk of time steps: (S, nc, D) rows of pitch ldgs = nu
+// rounded up to 4 (32-byte aligned rows for the tensor map)].  The chunk budget is 8 samples x one time step per SM; other
+// sample counts get proportionally more / fewer time steps per chunk.
+static int tiles_sms() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  return (long long)sizeof(double) * 4LL * D * nu * sms;
+  return sms;
+}
+static long long tiles_gchunk_doubles(int D, int nu, int sms) { return 8LL * sms * D * ((nu + 3) & ~3); }
+
+long long loglik_tiles_scratch_bytes(int D, int nu) {
+  const int sms = tiles_sms();
+  return (long long)sizeof(double) * (2LL * D * nu * sms + tiles_gchunk_doubles(D, nu, sms));
+}
+
+// G = A o (fmean + sqrt(fvar) o eps) for the samples / time steps of one chunk: slab z = s nc + (n - n0), D rows of pitch ldgs
+__global__ void __launch_bounds__(256) wishart_g_fill_kernel(const LikParams p, const int n0, const int nc, const int ldgs,
+                                                             double* __restrict__ Gc) {
+  const int R = p.D * p.nu;
+  const int z = blockIdx.y, s = z / nc, n = n0 + (z - s * nc);
+  const double* fm = p.fmean + (long long)n * p.ldf;
+  const double* fv = p.fvar + (long long)n * p.ldf;
+  const double* ep = p.eps + ((long long)s * p.N + n) * R;
+  double* G = Gc + (long long)z * p.D * ldgs;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = (blockIdx.x * 4 + u) * 256 + threadIdx.x;
+    if (r < R) {
+      const int d = r / p.nu, k = r - d * p.nu;
+      const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + k);
+      const double gm = a * fm[r], gs = a * sqrt(fv[r]);
+      G[d * ldgs + k] = gm + gs * __ldg(ep + r);
+    }
+  }
+}
+
+typedef CUresult (*LtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static LtEncodeTiledFn lt_encode_fn() {
+  static LtEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (LtEncodeTiledFn)ptr;
+  }
+  return fn;
 }
 
 template <int NB>
-static int launch_tiles_nb(const LikParams& p, cudaStream_t stream, int grid) {
-  const long long smem = (long long)lt_layout(NB).total * 8;
+static int launch_tiles_nb(const LikParams& p, cudaStream_t stream, int* part_rows) {
+  constexpr TilesLayout L = lt_layout(NB);
+  const long long smem = (long long)L.total * 8;
   auto kern = wishart_loglik_tiles_kernel<NB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid, LT_WARPS * 32, smem, stream>>>(p);
+  const int sms = tiles_sms();
+  const int ldgs = (p.nu + 3) & ~3;
+  const long long slab = (long long)p.D * ldgs;                               // doubles per (sample, time step)
+  long long NC = tiles_gchunk_doubles(p.D, p.nu, sms) / (slab * p.S);          // time steps per chunk
+  if (NC < 1) return FCEST_ERR_UNSUPPORTED;                                    // S > 8 sms samples
+  if (NC > p.N) NC = p.N;
+  const int grid = (int)(NC < sms ? NC : sms);                                 // the same CTAs (partial rows) in every chunk
+  double* Gc = p.ws + 2LL * p.D * p.nu * sms;
+  // tensor map over the chunk's G: (nu columns, D rows, S x NC slabs); a box is one panel = 4 columns x Dm rows of one
+  // slab, rows >= D and columns >= nu are zero-filled by the copy engine
+  LtEncodeTiledFn enc = lt_encode_fn();
+  if (!enc) return FCEST_ERR_UNSUPPORTED;
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)p.nu, (cuuint64_t)p.D, (cuuint64_t)(p.S * NC)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldgs * 8, (cuuint64_t)slab * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)LT_PC, (cuuint32_t)L.Dm, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)Gc, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return FCEST_ERR_ARGUMENT;
+  const int R = p.D * p.nu;
+  for (int n0 = 0; n0 < p.N; n0 += (int)NC) {
+    const int nc = p.N - n0 < NC ? p.N - n0 : (int)NC;
+    wishart_g_fill_kernel<<<dim3((R + 1023) / 1024, p.S * nc), 256, 0, stream>>>(p, n0, nc, ldgs, Gc);
+    FCEST_CHECK_LAUNCH();
+    kern<<<grid, LT_WARPS * 32, smem, stream>>>(tm, p, ldgs, Gc, n0, nc);
+    if (n0 + nc < p.N) FCEST_CHECK_LAUNCH();   // the caller counts / checks the last launch
+  }
+  *part_rows = grid;
   return 0;
 }
 
 int launch_loglik_tiles(LikParams p, cudaStream_t stream, int* part_rows) {
   if (!loglik_tiles_supported(p.D, p.nu)) return -1;
   if (p.ws == nullptr) return FCEST_ERR_ARGUMENT;
-  const int grid = tiles_grid(p.N);
-  p.ws_stride = 4LL * p.D * p.nu;
-  int rc = -1;
+  p.ws_stride = 2LL * p.D * p.nu;
   switch (tiles_capacity(p.D)) {
-    case 10: rc = launch_tiles_nb<10>(p, stream, grid); break;
-    case 14: rc = launch_tiles_nb<14>(p, stream, grid); break;
-    case 18: rc = launch_tiles_nb<18>(p, stream, grid); break;
-    case 22: rc = launch_tiles_nb<22>(p, stream, grid); break;
-    case 26: rc = launch_tiles_nb<26>(p, stream, grid); break;
+    case 10: return launch_tiles_nb<10>(p, stream, part_rows);
+    case 14: return launch_tiles_nb<14>(p, stream, part_rows);
+    case 18: return launch_tiles_nb<18>(p, stream, part_rows);
+    case 22: return launch_tiles_nb<22>(p, stream, part_rows);
+    case 26: return launch_tiles_nb<26>(p, stream, part_rows);
     default: return -1;
   }
-  if (rc == 0) *part_rows = grid;
-  return rc;
 }
 
 }  // namespace fcest
