@@ -146,13 +146,13 @@ __device__ __forceinline__ const double* cl_tile(const ClCtx<C>& c) {
 template <int C>
 __device__ __forceinline__ void cl_load_g(const ClCtx<C>& c, int ib, double (&g)[2]) {
   const int d = 8 * ib + c.gid;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int k = c.colC + e;
-    double v = 0.0;
-    if (d < c.D && k < c.nu) v = c.G[d * c.ldgs + k];
-    else if (d == c.D && k == c.ycol) v = 1.0;
-    g[e] = v;
+  double2 v2 = make_double2(0.0, 0.0);
+  if (d < c.D && c.colC < c.nu) v2 = *reinterpret_cast<const double2*>(c.G + d * c.ldgs + c.colC);   // one 16-byte load
+  g[0] = v2.x;
+  g[1] = (c.colC + 1 < c.nu) ? v2.y : 0.0;   // odd nu: the pad column of the slab is not written
+  if (d == c.D) {
+    if (c.colC == c.ycol) g[0] = 1.0;
+    if (c.colC + 1 == c.ycol) g[1] = 1.0;
   }
 }
 

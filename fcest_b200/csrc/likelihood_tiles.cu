@@ -110,13 +110,13 @@ struct LtCtx {
 // G tile (ib, cb) in accumulator layout; column ycol carries e_D
 __device__ __forceinline__ void lt_load_g(const LtCtx& c, int ib, double (&g)[2]) {
   const int d = 8 * ib + c.gid;
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int k = c.colC + e;
-    double v = 0.0;
-    if (d < c.D && k < c.nu) v = c.G[d * c.ldgs + k];
-    else if (d == c.D && k == c.ycol) v = 1.0;
-    g[e] = v;
+  double2 v2 = make_double2(0.0, 0.0);
+  if (d < c.D && c.colC < c.nu) v2 = *reinterpret_cast<const double2*>(c.G + d * c.ldgs + c.colC);   // one 16-byte load
+  g[0] = v2.x;
+  g[1] = (c.colC + 1 < c.nu) ? v2.y : 0.0;   // odd nu: the pad column of the slab is not written
+  if (d == c.D) {
+    if (c.colC == c.ycol) g[0] = 1.0;
+    if (c.colC + 1 == c.ycol) g[1] = 1.0;
   }
 }
 
@@ -361,17 +361,39 @@ wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikPa
       for (int jb = 0; jb < NB; ++jb) {
         // (a) column jb: S[ib][jb] -= sum_{kb < jb} L[ib][kb] L[jb][kb]^T ; up to four tiles per warp in flight
         {
-          double c[4][2];
+          double c[4][2], c2[4][2];   // two partial sums per tile (even / odd kb): half the dependent DMMA chain
           int ibs[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             ibs[t] = jb + warp + t * LT_WARPS;
+            c2[t][0] = c2[t][1] = 0.0;
             if (ibs[t] < NB) {
               const double2 v = *reinterpret_cast<const double2*>(tiles + TI(ibs[t], jb) * 64 + oC);
               c[t][0] = v.x; c[t][1] = v.y;
             } else { c[t][0] = c[t][1] = 0.0; }
           }
-          for (int kb = 0; kb < jb; ++kb) {
+          int kb = 0;
+          for (; kb + 1 < jb; kb += 2) {
+            const double* Tj = tiles + TI(jb, kb) * 64;   // tiles (jb, kb), (jb, kb + 1) are adjacent
+            const double nb0 = -Tj[oA0], nb1 = -Tj[oA1], nd0 = -Tj[64 + oA0], nd1 = -Tj[64 + oA1];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (ibs[t] < NB) {
+                const double* Ti = tiles + TI(ibs[t], kb) * 64;
+                dmma(c[t][0], c[t][1], Ti[oA0], nb0);
+                dmma(c2[t][0], c2[t][1], Ti[64 + oA0], nd0);
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (ibs[t] < NB) {
+                const double* Ti = tiles + TI(ibs[t], kb) * 64;
+                dmma(c[t][0], c[t][1], Ti[oA1], nb1);
+                dmma(c2[t][0], c2[t][1], Ti[64 + oA1], nd1);
+              }
+            }
+          }
+          if (kb < jb) {
             const double* Tj = tiles + TI(jb, kb) * 64;
             const double nb0 = -Tj[oA0], nb1 = -Tj[oA1];
 #pragma unroll
@@ -383,7 +405,8 @@ wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikPa
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            if (ibs[t] < NB) *reinterpret_cast<double2*>(tiles + TI(ibs[t], jb) * 64 + oC) = make_double2(c[t][0], c[t][1]);
+            if (ibs[t] < NB)
+              *reinterpret_cast<double2*>(tiles + TI(ibs[t], jb) * 64 + oC) = make_double2(c[t][0] + c2[t][0], c[t][1] + c2[t][1]);
         }
         __syncthreads();
         // (b) diagonal tile -> I_jj = L_jj^-1 (in place), dinv
