@@ -536,6 +536,8 @@ tri_syrk_smem_kernel(const double* __restrict__ q_sqrt, int M, double* __restric
 // block-row order, so the 32 warps of a CTA work on two or three block rows at a time and the 13 KB of Gs they share
 // stay in L1; the packed cotangent is then read from L2 about once.
 // ---------------------------------------------------------------------------------------------
+constexpr int TG_NC = 4;   // column blocks per work unit of tri_grad_smem_kernel
+
 template <bool ADAM>
 __global__ void __launch_bounds__(TSM_WARPS * 32, 1)
 tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double* __restrict__ q_sqrt, int M,
@@ -566,13 +568,15 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
     for (int i = warp; i < M; i += TSM_WARPS)
       for (int j = i + 1 + lane; j < M; j += 32) dq[(long long)i * M + j] = 0.0;
   }
-  // unit table: block rows from the bottom, column pairs left to right (heavy first within a row)
+  // unit table: block rows from the bottom, groups of TG_NC column blocks left to right (heavy first within a row);
+  // one A fragment pair feeds up to TG_NC output tiles (half the non-DMMA instructions per DMMA of the pair version:
+  // 0.93 -> 0.88 ms; pairing two block rows on top of it, for half the B reads, was slower: 0.95 ms at the 64-register cap)
   int nunits = 0;
-  for (int ib = 0; ib < nb; ++ib) nunits += ib / 2 + 1;
+  for (int ib = 0; ib < nb; ++ib) nunits += ib / TG_NC + 1;
   for (int u = tid; u < nunits; u += blockDim.x) {
     int ib = nb - 1, rem = u;
-    while (rem >= ib / 2 + 1) { rem -= ib / 2 + 1; --ib; }
-    units[u] = (unsigned short)((ib << 8) | (2 * rem));
+    while (rem >= ib / TG_NC + 1) { rem -= ib / TG_NC + 1; --ib; }
+    units[u] = (unsigned short)((ib << 8) | (TG_NC * rem));
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -586,11 +590,13 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= nunits) break;
     const int ib = units[idx] >> 8, jb0 = units[idx] & 255;
-    const bool two = jb0 + 1 <= ib;
+    const int ncol = min(TG_NC, ib + 1 - jb0);   // output tiles (ib, jb0 .. jb0 + ncol - 1)
     const int i = 8 * ib + gid;
     const bool iok = i < M;
     const double* Gi = G + (long long)i * (i + 1) / 2;   // packed row i (columns <= i)
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    double c[TG_NC][2];
+#pragma unroll
+    for (int t = 0; t < TG_NC; ++t) c[t][0] = c[t][1] = 0.0;
     for (int kb = jb0; kb < nb; ++kb) {
       // A fragment: Gs[i][k], k = 8 kb + tig (+ 4)
       const int k0 = 8 * kb + tig, k1 = k0 + 4;
@@ -608,12 +614,13 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
         if (k1 == i) a1 = 2.0 * a1 - kl;
       }
       const double* pb = Lb + (size_t)(kb * (kb + 1) / 2 + jb0) * 64;   // block (kb, jb0); (kb, jb0 + 1) follows
-      dmma(c00, c01, a0, pb[ob0]);
-      dmma(c00, c01, a1, pb[ob1]);
-      if (two && kb > jb0) {
-        dmma(c10, c11, a0, pb[64 + ob0]);
-        dmma(c10, c11, a1, pb[64 + ob1]);
-      }
+      const int nact = min(ncol, kb - jb0 + 1);   // block (kb, jb0 + t) is zero above the diagonal
+#pragma unroll
+      for (int t = 0; t < TG_NC; ++t)
+        if (t < nact) dmma(c[t][0], c[t][1], a0, pb[t * 64 + ob0]);
+#pragma unroll
+      for (int t = 0; t < TG_NC; ++t)
+        if (t < nact) dmma(c[t][0], c[t][1], a1, pb[t * 64 + ob1]);
     }
     if (iok) {
       const long long rbase = (long long)r_lat * M * M + (long long)i * M;
@@ -636,13 +643,13 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
           dq_sqrt[rbase + col] = v0;
         }
       };
-      const int col0 = 8 * jb0 + 2 * tig;
-      if (col0 + 1 <= i) emit(col0, c00, col0 + 1 == i ? c01 + dinv : c01, true);
-      else if (col0 == i) emit(col0, c00 + dinv, 0.0, false);
-      if (two) {
-        const int col1 = col0 + 8;
-        if (col1 + 1 <= i) emit(col1, c10, col1 + 1 == i ? c11 + dinv : c11, true);
-        else if (col1 == i) emit(col1, c10 + dinv, 0.0, false);
+#pragma unroll
+      for (int t = 0; t < TG_NC; ++t) {
+        if (t < ncol) {
+          const int col = 8 * (jb0 + t) + 2 * tig;
+          if (col + 1 <= i) emit(col, c[t][0], col + 1 == i ? c[t][1] + dinv : c[t][1], true);
+          else if (col == i) emit(col, c[t][0] + dinv, 0.0, false);
+        }
       }
     }
   }
