@@ -33,8 +33,19 @@
 
 namespace fcest {
 
-constexpr int LT_WARPS = 8;
-constexpr int LT_MQ = 6;     // macro tiles per warp and SYRK pass
+// Warps per CTA, by row-block capacity: as many as give the column-block phase (P4, latency bound: one warp per 8-column
+// block of G) a balanced hand-out -- NB column blocks on NB / 2 or NB warps -- at 128 - 168 registers per thread.
+// D = 200: 8 warps 36.1 ms, 10 warps 34.5 ms, 13 warps 31.6 ms.
+#ifndef FCEST_LT_W26
+#define FCEST_LT_W26 13
+#endif
+__host__ __device__ constexpr int lt_warps(int NB) { return NB == 26 ? FCEST_LT_W26 : NB == 22 ? 11 : NB == 18 ? 9 : NB == 14 ? 14 : 10; }
+// macro tiles per warp and SYRK pass (16 accumulator registers each)
+__host__ __device__ constexpr int lt_mq(int NB) {
+  const int nbm = (NB + 1) / 2, nmac = nbm * (nbm + 1) / 2, w = lt_warps(NB);
+  const int per = (nmac + w - 1) / w;
+  return per > 4 ? (per + 1) / 2 > 4 ? 4 : (per + 1) / 2 : per;
+}
 constexpr int LT_PC = 4;     // columns of a G panel = one DMMA k-step (dense 32-byte rows: fragment reads are contiguous)
 constexpr int LT_ST = 6;     // panel stages in the TMA ring
 
@@ -52,7 +63,7 @@ __host__ __device__ constexpr TilesLayout lt_layout(int NB) {
   L.NT = L.NB * (L.NB + 1) / 2;
   L.off_pan = L.NT * 64;
   int pan = LT_ST * L.Dm * LT_PC;                   // panel ring (P1); reused as 8 x Dp row-sum partials (P4)
-  if (pan < LT_WARPS * L.Dp) pan = LT_WARPS * L.Dp;
+  if (pan < lt_warps(NB) * L.Dp) pan = lt_warps(NB) * L.Dp;
   L.off_vec = L.off_pan + pan;
   L.off_bar = L.off_vec + 4 * L.Dp + 16;            // dinv, yv, spl, alpha, misc
   L.total = L.off_bar + 2 * LT_ST;                  // full / empty mbarriers
@@ -220,7 +231,7 @@ __device__ __forceinline__ void lt_epilogue(double (&acc)[NB][2], const LtCtx& c
 }
 
 template <int NB>
-__global__ void __launch_bounds__(LT_WARPS * 32, 1)
+__global__ void __launch_bounds__(lt_warps(NB) * 32, 1)
 wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikParams p, const int ldgs, const double* Gc,
                             const int n0, const int nc) {
   extern __shared__ __align__(128) double sm[];
@@ -228,6 +239,7 @@ wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikPa
   constexpr TilesLayout L = lt_layout(NB);
   constexpr int Dp = L.Dp, Dm = L.Dm;
   constexpr int STAGE = Dm * LT_PC;   // doubles per panel stage
+  constexpr int LT_WARPS = lt_warps(NB), LT_MQ = lt_mq(NB);
   double* tiles = sm;
   double* pan = sm + L.off_pan;
   double* dinv = sm + L.off_vec;
@@ -268,7 +280,7 @@ wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikPa
   const bool vec = (nu & 1) == 0;
 
   for (int d = tid; d < Dp; d += blockDim.x) spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
-  double glam_acc = 0.0;  // thread d < D (blockDim = 256 >= D)
+  double glam_acc = 0.0;  // thread d < D (blockDim = 32 lt_warps(NB) >= 8 NB > D)
 
   for (int n = n0 + blockIdx.x; n < n0 + nc; n += gridDim.x) {
     const double* fm = p.fmean + (long long)n * p.ldf;
@@ -621,7 +633,7 @@ static int launch_tiles_nb(const LikParams& p, cudaStream_t stream, int* part_ro
     const int nc = p.N - n0 < NC ? p.N - n0 : (int)NC;
     wishart_g_fill_kernel<<<dim3((R + 1023) / 1024, p.S * nc), 256, 0, stream>>>(p, n0, nc, ldgs, Gc);
     FCEST_CHECK_LAUNCH();
-    kern<<<grid, LT_WARPS * 32, smem, stream>>>(tm, p, ldgs, Gc, n0, nc);
+    kern<<<grid, lt_warps(NB) * 32, smem, stream>>>(tm, p, ldgs, Gc, n0, nc);
     if (n0 + nc < p.N) FCEST_CHECK_LAUNCH();   // the caller counts / checks the last launch
   }
   *part_rows = grid;
