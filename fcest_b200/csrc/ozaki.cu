@@ -329,16 +329,21 @@ ozaki_gemm_kernel(const Params p) {
 #pragma unroll
       for (int ps = 0; ps < S::NPASS; ++ps) {
         const int nbuf = S::d_hi(ps) - S::d_lo(ps) + 1;
+        // The accumulators of the pass must have been drained by the epilogue.  BOTH issuers observe every hand-back, at
+        // the top of every pass: a parity wait cannot tell "two phases behind" from "done", and with a single-stage pass
+        // (short contractions) the warp that does not issue it would otherwise skip a phase of accumulator 0 -- it then
+        // overwrote an accumulator the epilogue was still reading (wrong results at K = 384 with 5 digits, dead-locks at
+        // K = 128 / 192 / 225 with 7 / 6 / 5 digits; tools/ozaki_smallk_check.py, test_ozaki_short_contractions)
+        if (kb0 < kb1) {
+          if (nbuf > 0) mbar_wait_t(tempty + 0, (use0 & 1u) ^ 1u, w_te, dbg);
+          if (nbuf > 1) mbar_wait_t(tempty + 8, (use1 & 1u) ^ 1u, w_te, dbg);
+          if (nbuf > 2) mbar_wait_t(tempty + 16, (use2 & 1u) ^ 1u, w_te, dbg);
+          if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
+        }
         for (int kb = kb0; kb < kb1; kb += S::kbs(ps)) {
           const int g = kb1 - kb < S::kbs(ps) ? kb1 - kb : S::kbs(ps);   // K blocks in this stage
           const uint32_t n = 2u * S::nsl(ps) * g;
           if ((seq & 1u) == me) {
-            if (kb == kb0) {   // first stage of the pass: its accumulators must have been drained by the epilogue
-              if (nbuf > 0) mbar_wait_t(tempty + 0, (use0 & 1u) ^ 1u, w_te, dbg);
-              if (nbuf > 1) mbar_wait_t(tempty + 8, (use1 & 1u) ^ 1u, w_te, dbg);
-              if (nbuf > 2) mbar_wait_t(tempty + 16, (use2 & 1u) ^ 1u, w_te, dbg);
-              if (nbuf > 3) mbar_wait_t(tempty + 24, (use3 & 1u) ^ 1u, w_te, dbg);
-            }
             mbar_wait_t(full + 8 * (seq & (NBAR - 1)), (seq >> NBAR_LOG) & 1u, w_f, dbg);
             const long long t_ready = dbg ? clock64() : 0;
             if (seq > 0) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");   // stage seq - 1 has been issued
@@ -686,18 +691,18 @@ ozaki_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int ps = 0; ps < S::NPASS; ++ps) {
           const int nbuf = S::d_hi(ps) - S::d_lo(ps) + 1;
           const int nsl = S::nsl(ps);
+          if (kb0 < kb1) {   // both issuers observe every hand-back of the pass's accumulators (see the single-CTA kernel)
+            const long long t0 = dbg ? clock64() : 0;
+            if (nbuf > 0) mbar_wait_cluster(tempty + 0, (use0 & 1u) ^ 1u);
+            if (nbuf > 1) mbar_wait_cluster(tempty + 8, (use1 & 1u) ^ 1u);
+            if (nbuf > 2) mbar_wait_cluster(tempty + 16, (use2 & 1u) ^ 1u);
+            if (nbuf > 3) mbar_wait_cluster(tempty + 24, (use3 & 1u) ^ 1u);
+            if (dbg) w_te += clock64() - t0;
+          }
           for (int kb = kb0; kb < kb1; kb += S::kbs(ps)) {
             const int g = kb1 - kb < S::kbs(ps) ? kb1 - kb : S::kbs(ps);
             const uint32_t n = stage_slots2(nsl, g);
             if ((seq & 1u) == me) {
-              if (kb == kb0) {   // first stage of the pass: both CTAs' epilogues have drained its accumulators
-                const long long t0 = dbg ? clock64() : 0;
-                if (nbuf > 0) mbar_wait_cluster(tempty + 0, (use0 & 1u) ^ 1u);
-                if (nbuf > 1) mbar_wait_cluster(tempty + 8, (use1 & 1u) ^ 1u);
-                if (nbuf > 2) mbar_wait_cluster(tempty + 16, (use2 & 1u) ^ 1u);
-                if (nbuf > 3) mbar_wait_cluster(tempty + 24, (use3 & 1u) ^ 1u);
-                if (dbg) w_te += clock64() - t0;
-              }
               mbar_wait_t(full + 8 * (seq & (NBAR2 - 1)), (seq >> NBAR2_LOG) & 1u, w_f, dbg);
               const long long t_ready = dbg ? clock64() : 0;
               if (seq > 0) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((seq - 1u) & 1u)) : "memory");

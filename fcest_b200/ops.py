@@ -62,7 +62,9 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 GEMM_IMPL = os.environ.get("FCEST_GEMM_IMPL", "ozaki")
 OZAKI_SLICES = int(os.environ.get("FCEST_OZAKI_SLICES", "6"))
 OZAKI_SLICES_BWD = int(os.environ.get("FCEST_OZAKI_SLICES_BWD", "5"))
-OZAKI_MIN_FLOPS = 4e9
+OZAKI_MIN_FLOPS = float(os.environ.get("FCEST_OZAKI_MIN_FLOPS", "4e9"))
+OZAKI_MIN_DIM = int(os.environ.get("FCEST_OZAKI_MIN_DIM", "128"))   # smallest output dimension / contraction length
+OZAKI_MIN_K = int(os.environ.get("FCEST_OZAKI_MIN_K", "192"))     # that still goes to the int8 path (C2: 461 -> 667 evals/s)
 
 
 def dgemm_ozaki(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C, alpha=1.0, bias_row=None,
@@ -84,7 +86,7 @@ def dgemm(a_kmajor: bool, b_kmajor: bool, M: int, N: int, K: int, A, B, C, alpha
     """C[:M,:N] = alpha op(A) op(B) + beta C (+ biases); see ``fcest_dgemm`` in the header.  ``backward`` marks a
     gradient GEMM (fewer digits on the int8 path)."""
     if (GEMM_IMPL == "ozaki" and beta == 0.0 and bias_col is None and 2.0 * M * N * K >= OZAKI_MIN_FLOPS
-            and min(M, N) >= 256 and K >= 512):
+            and min(M, N) >= OZAKI_MIN_DIM and K >= OZAKI_MIN_K):
         return dgemm_ozaki(a_kmajor, b_kmajor, M, N, K, A, B, C, alpha=alpha, bias_row=bias_row,
                            slices=OZAKI_SLICES_BWD if backward else OZAKI_SLICES)
     lib = _lib.load_library()

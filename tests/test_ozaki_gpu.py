@@ -123,3 +123,30 @@ def test_ozaki_non_finite_operands_give_nan_rows(cuda):
     ref = A[keep] @ B[keepc].t()
     assert torch.isfinite(C[keep][:, keepc]).all()
     assert float((C[keep][:, keepc] - ref).abs().max() / ref.abs().max()) < 1e-10
+
+
+@pytest.mark.timeout(180, method="thread")
+@pytest.mark.parametrize("slices,K", [(7, 128), (6, 192), (5, 225), (5, 384), (6, 64), (4, 100)])
+def test_ozaki_short_contractions(cuda, slices, K):
+    """Short contractions with several work units per CTA: the second accumulator pass is a single stage, issued by ONE of
+    the two MMA-issuing warps.  Before both issuers observed every accumulator hand-back this gave wrong results
+    (K = 384, 5 digits) or dead-locked (K = 128 / 192 / 225): the other warp skipped a phase of the accumulator-free
+    barrier (a parity wait cannot tell two phases behind from done)."""
+    from fcest_b200 import ops
+    g = torch.Generator().manual_seed(K + slices)
+    M, N = 1200, 20100   # 1580 output tiles on 148 SMs
+    A = ops.as_pitched(torch.randn(M, K, dtype=torch.float64, generator=g).cuda())
+    B = ops.as_pitched(torch.randn(K, N, dtype=torch.float64, generator=g).cuda())
+    ref = ops.pitched(M, N, "cuda")
+    got = ops.pitched(M, N, "cuda")
+    impl = ops.GEMM_IMPL
+    try:
+        ops.GEMM_IMPL = "dmma"
+        ops.dgemm(True, False, M, N, K, A, B, ref)
+    finally:
+        ops.GEMM_IMPL = impl
+    for _ in range(2):
+        ops.dgemm_ozaki(True, False, M, N, K, A, B, got, slices=slices)
+    torch.cuda.synchronize()
+    rel = float((got - ref).abs().max() / ref.abs().max())
+    assert rel < {4: 1e-6, 5: 1e-8, 6: 1e-10, 7: 1e-12}[slices], (slices, K, rel)
