@@ -48,8 +48,19 @@ namespace cg = cooperative_groups;
 
 namespace fcest {
 
-constexpr int CL_WARPS = 8;   // warps per CTA
-constexpr int CL_MQ = 6;      // macro tiles per warp and SYRK pass
+// Warps per CTA by (capacity, cluster size): the column-block phase (one warp per 8-column block of G) is latency bound
+// and wants as many warps as blocks -- 42 / 46 blocks on 4 x 11 / 4 x 12 warps in ONE round (D = 320: 35.5 -> 33.9 ms)
+// -- where the per-warp row-sum scratch (8 NB doubles each) still fits beside the tile store.  CTA pairs stay at 8 warps:
+// 13 warps at 128 registers spill 17 - 24 KB per thread in the unrolled substitution (D = 256: 24.8 -> 30.9 ms).
+__host__ __device__ constexpr int cl_warps(int NB, int C) {
+  return C == 2 ? 8 : (NB <= 42 ? 11 : NB <= 46 ? 12 : 8);
+}
+// macro tiles per warp and SYRK pass (16 accumulator registers each)
+__host__ __device__ constexpr int cl_mq(int NB, int C) {
+  const int nbm = (NB + 1) / 2, nmac = nbm * (nbm + 1) / 2, cw = C * cl_warps(NB, C);
+  const int per = (nmac + cw - 1) / cw;
+  return cl_warps(NB, C) == 8 ? 6 : (per > 4 ? ((per + 1) / 2 > 4 ? 4 : (per + 1) / 2) : per);
+}
 constexpr int CL_PC = 4;      // columns of a G panel = one DMMA k-step (pitch 4: fragment reads are contiguous)
 constexpr int CL_MAXST = 8;   // at most 8 panel stages
 constexpr int CL_PF = 3;      // G tiles in flight ahead of the forward substitution
@@ -85,7 +96,7 @@ __host__ __device__ constexpr ClLayout cl_layout(int NB) {
   int st = avail / stage;
   if (st > CL_MAXST) st = CL_MAXST;
   if (st < 2) st = 2;
-  while (st * stage < CL_WARPS * L.Dp) ++st;          // the ring doubles as 8 x Dp row-sum partials in P4
+  while (st * stage < cl_warps(NB, C) * L.Dp) ++st;   // the ring doubles as per-warp row-sum partials (Dp each) in P4
   L.ST = st;
   L.off_vec = L.off_pan + st * stage;
   L.off_bar = L.off_vec + vec;
@@ -319,7 +330,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 }
 
 template <int NB, int C>
-__global__ void __launch_bounds__(CL_WARPS * 32, 1)
+__global__ void __launch_bounds__(cl_warps(NB, C) * 32, 1)
 wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const LikParams p, const int ldgs, const int box_rows) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(128) double sm[];
@@ -327,6 +338,7 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
   constexpr ClLayout L = cl_layout<C>(NB);
   constexpr int Dp = L.Dp, Dm = L.Dm, ST = L.ST;
   constexpr int STAGE = Dm * CL_PC;   // doubles per panel stage
+  constexpr int CL_WARPS = cl_warps(NB, C), CL_MQ = cl_mq(NB, C);
   double* tiles = sm;
   double* pan = sm + L.off_pan;
   double* dinv = sm + L.off_vec;
@@ -737,6 +749,7 @@ inline ClEncodeTiledFn cl_encode_fn() {
 template <int NB, int C>
 int launch_cluster_nb(const LikParams& p, cudaStream_t stream, int* part_rows) {
   constexpr ClLayout L = cl_layout<C>(NB);
+  static_assert((long long)L.total * 8 + 64 <= 227 * 1024, "tile store + ring + vectors exceed the shared memory of an SM");
   const long long smem = (long long)L.total * 8;
   auto kern = wishart_loglik_cluster_kernel<NB, C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -751,7 +764,7 @@ int launch_cluster_nb(const LikParams& p, cudaStream_t stream, int* part_rows) {
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.gridDim = dim3((unsigned)(sms / C * C), 1, 1);
-  cfg.blockDim = dim3(CL_WARPS * 32, 1, 1);
+  cfg.blockDim = dim3(cl_warps(NB, C) * 32, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = stream;
   cfg.attrs = at;
