@@ -131,6 +131,13 @@ def test_loglik_large_D(cuda, D):
     _check(N=2, D=D, S=2, seed=D)
 
 
+def test_loglik_large_D_odd_size_and_vector_A(cuda):
+    """Cluster-tiled kernel with an odd D (odd row pitch of the noise: no bulk L2 prefetch, padded G slot rows for the tensor
+    map) and with the vector form of A; three time steps on at most two clusters' worth of CTAs."""
+    _check(N=3, D=233, S=3, seed=233, vector_a=True)
+    _check(N=2, D=305, S=2, seed=305)
+
+
 def test_large_D_prediction_and_pd_check(cuda):
     """predict moments and the batched PD check at D = 256 and 400 against the oracle."""
     from fcest_b200 import ops
