@@ -146,6 +146,38 @@ def build_model(seed, device):
     return m, p["x"], p["y"]
 
 
+def measure_likelihood_large(dev):
+    """Likelihood kernels of the larger sizes (outside the timed region, rank 0 at N = 1): the shared-memory-tiled kernel at
+    the C5 size D = 200 and the cluster-tiled kernel at D = 256, forward + backward, CUDA events around the C-ABI call."""
+    from fcest_b200 import ops as _o
+    out = []
+    for D, N, S, kernel in ((200, 296, 8, "wishart_loglik_tiles_kernel<26> + wishart_g_fill_kernel (TMA panel ring, precomputed G)"),
+                            (256, 296, 8, "wishart_loglik_cluster_kernel<34, 2> (tiles in the distributed shared memory of a CTA pair)")):
+        R = D * D
+        g = torch.Generator(device=dev).manual_seed(D)
+        fm = _o.pitched(N, R, dev); fm.copy_(0.3 * torch.randn(N, R, dtype=torch.float64, device=dev, generator=g))
+        fv = _o.pitched(N, R, dev); fv.copy_(0.05 + torch.rand(N, R, dtype=torch.float64, device=dev, generator=g))
+        y = torch.randn(N, D, dtype=torch.float64, device=dev, generator=g)
+        A = torch.eye(D, dtype=torch.float64, device=dev) + 0.2 * torch.randn(D, D, dtype=torch.float64, device=dev, generator=g)
+        lam = torch.full((D,), -4.6, dtype=torch.float64, device=dev)
+        eps = torch.randn(S, N, R, dtype=torch.float64, device=dev, generator=g)   # 0.76 / 1.24 GB: larger than L2
+        for _ in range(2):
+            o = _o.wishart_loglik(fm, fv, eps, y, A, lam)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); o = _o.wishart_loglik(fm, fv, eps, y, A, lam); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[1]
+        fl = 11.0 / 3.0 * D ** 3 * S * N
+        out.append({"D": D, "N": N, "S": S, "kernel": kernel, "ms": ms, "algorithmic_flops": fl,
+                    "achieved": fl / (ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "cholesky_ok": bool(int(o["info"].max().item()) == 0)})
+        del fm, fv, eps, o
+        torch.cuda.empty_cache()
+    return out
+
+
 def measure_fp64_peak(dev):
     """cuBLAS DGEMM 8192^3 through torch.matmul (2 N^3 flop), best of 10 after 2 warm-up calls, CUDA events: the
     fp64 roofline denominator, measured in this run on this GPU (MEASURED_PEAKS.json carries no fp64 figure)."""
@@ -523,6 +555,7 @@ def run_cuda(args):
     del model
     torch.cuda.empty_cache()
     strong = strong_scaling_block(dev, rank, world, K, t_ms / K) if world > 1 else None
+    lik_large = measure_likelihood_large(dev) if (rank == 0 and world == 1) else None
 
     if rank == 0:
         peak_file = json.load(open(FP64_PEAK_FILE))["fp64_tflops"] if os.path.exists(FP64_PEAK_FILE) else None
@@ -599,6 +632,8 @@ def run_cuda(args):
                                     "peak": peak, "unit": "TFLOP/s",
                                     "frac": (flops["likelihood"] / (lik_ms * 1e-3) * 1e-12 / peak) if lik_ms else None},
             "roofline_window_cov": wcov,
+            "roofline_likelihood_large": ([dict(r, peak=peak, frac=r["achieved"] / peak) for r in lik_large]
+                                          if lik_large else None),
             "per_call_ms": {k: round(v, 4) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
             "elbo_last": last, "cholesky_ok": info_ok,
         }
