@@ -659,6 +659,7 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
 // dP[:, n] (+)= 2 T_n p_n - 2 gs[n] p_n * use_prior,   T_n symmetric from packed Tk[n, idx(i,j)].
 // gs[n] = sum_r g_var[n, r] (row sums, computed here).   grid = N, block = 256, smem = 2M + 32
 // ---------------------------------------------------------------------------------------------
+template <int MAXC>   // columns per lane: M <= 32 MAXC
 __global__ void sym_matvec_kernel(const double* __restrict__ Tk, long long ldk,
                                   const double* __restrict__ P, long long ldp, int M, int N,
                                   const double* __restrict__ g_var, long long ldg, int R,
@@ -679,26 +680,42 @@ __global__ void sym_matvec_kernel(const double* __restrict__ Tk, long long ldk,
   // single pass over the packed lower triangle, one warp per row i (coalesced): lane j accumulates
   //   row part    acc_row  += T[i,j] p[j]          (warp-reduced -> out[i])
   //   column part col[j]   += T[i,j] p[i], j < i   (lane-private registers, columns j = lane + 32 c)
-  constexpr int MAXC = 13;  // M <= 416
   double col[MAXC];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) col[c] = 0.0;
   double* colpart = red + 32;  // nwarps x M per-warp column partials (no atomics: deterministic)
-  for (int i = warp; i < M; i += nwarps) {
-    const double* Ti = T + (long long)i * (i + 1) / 2;
-    const double pi = p[i];
-    double s = 0.0;
+  // four rows of a warp in flight (loads of all four issued before the first use; same order of additions as row by row)
+  constexpr int RU = 4;
+  for (int i0 = warp; i0 < M; i0 += RU * nwarps) {
+    double t[RU][MAXC];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      const int j = lane + 32 * c;
-      if (j <= i) {
-        const double t = Ti[j];
-        s += t * p[j];
-        if (j < i) col[c] += t * pi;
+    for (int u = 0; u < RU; ++u) {
+      const int i = i0 + u * nwarps;
+      const double* Ti = T + (long long)i * (i + 1) / 2;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int j = lane + 32 * c;
+        t[u][c] = (i < M && j <= i) ? Ti[j] : 0.0;
       }
     }
-    s = warp_sum(s);
-    if (lane == 0) acc[i] = s;
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int i = i0 + u * nwarps;
+      if (i < M) {   // warp-uniform
+        const double pi = p[i];
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const int j = lane + 32 * c;
+          if (j <= i) {
+            s += t[u][c] * p[j];
+            if (j < i) col[c] += t[u][c] * pi;
+          }
+        }
+        s = warp_sum(s);
+        if (lane == 0) acc[i] = s;
+      }
+    }
   }
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
@@ -832,10 +849,17 @@ extern "C" int fcest_sym_matvec(const double* Tk, long long ldk, const double* P
   if (N <= 0) return 0;
   const size_t smem = sizeof(double) * (2 * M + 32 + 8 * M);
   if (smem > 200 * 1024 || M > 416) return FCEST_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(sym_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  sym_matvec_kernel<<<N, 256, smem, stream>>>(Tk, ldk, P, ldp, M, N, g_var, ldg, R, use_prior, dP,
-                                              lddp, gs_out, accumulate);
+  if (M <= 224) {   // 7 columns per lane: 56 instead of 104 registers for the four rows in flight
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(sym_matvec_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sym_matvec_kernel<7><<<N, 256, smem, stream>>>(Tk, ldk, P, ldp, M, N, g_var, ldg, R, use_prior, dP, lddp, gs_out,
+                                                   accumulate);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(sym_matvec_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sym_matvec_kernel<13><<<N, 256, smem, stream>>>(Tk, ldk, P, ldp, M, N, g_var, ldg, R, use_prior, dP, lddp, gs_out,
+                                                    accumulate);
+  }
   FCEST_CHECK_LAUNCH();
   return 0;
 }
