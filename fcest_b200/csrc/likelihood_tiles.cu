@@ -246,7 +246,6 @@ wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikPa
   double* yv = dinv + Dp;
   double* spl = yv + Dp;
   double* alpha = spl + Dp;
-  double* misc = alpha + Dp;
   __shared__ int bad_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
@@ -277,7 +276,6 @@ wishart_loglik_tiles_kernel(const __grid_constant__ CUtensorMap tmG, const LikPa
     lt_tma_load_3d(pan_u32 + stage * STAGE * 8, &tmG, full_bar + 8 * stage, k0, 0, z);
   };
   const int ycol = nu, ncb = nu / 8 + 1;  // column `nu` carries e_D (its solution is -alpha)
-  const bool vec = (nu & 1) == 0;
 
   for (int d = tid; d < Dp; d += blockDim.x) spl[d] = d < D ? softplus_d(p.lam[d]) : 1.0;
   double glam_acc = 0.0;  // thread d < D (blockDim = 32 lt_warps(NB) >= 8 NB > D)
@@ -538,13 +536,6 @@ bool loglik_tiles_supported(int D, int nu) {
   const int NB = tiles_capacity(D);
   if (!NB) return false;
   return (long long)lt_layout(NB).total * 8 + 64 <= kSmemLimitT;
-}
-
-static int tiles_grid(int N) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return N < sms ? N : sms;
 }
 
 // Scratch layout: [U1, U2 slots: 2 R doubles per CTA][G of one chunk of time steps: (S, nc, D) rows of pitch ldgs = nu
