@@ -37,6 +37,10 @@ int launch_loglik_tiles(LikParams p, cudaStream_t stream, int* part_rows);
 bool loglik_tiles_supported(int D, int nu);
 long long loglik_tiles_scratch_bytes(int D, int nu);
 
+// G = A o (fmean + sqrt(fvar) o eps) for all samples of the time steps [n0, n0 + nc): slab z = s nc + (n - n0) of Gc, D rows of
+// pitch ldgs (likelihood_tiles.cu; shared by the tiles and the cluster-tiled kernels).  Returns 0 or a cudaError_t.
+int launch_loglik_g_fill(const LikParams& p, int n0, int nc, int ldgs, double* Gc, cudaStream_t stream);
+
 // Cluster-tiled variant (likelihood_cluster.cu), 8 <= D <= 407: one thread-block cluster per matrix, the factor's
 // tiles in the distributed shared memory of the cluster.  p.ws must point to loglik_cluster_scratch_bytes(D, nu) bytes.
 int launch_loglik_cluster(LikParams p, cudaStream_t stream, int* part_rows);

@@ -35,9 +35,8 @@ long long loglik_cluster_scratch_bytes(int D, int nu) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  return (long long)sizeof(double) * cluster_slot_doubles(D, nu) * (sms / 2);   // clusters of two at most
+  return (long long)sizeof(double) * (cluster_slot_doubles(D, nu) * (sms / 2) + cluster_gchunk_doubles(D, nu, sms));
 }
-
 
 int launch_loglik_cluster(LikParams p, cudaStream_t stream, int* part_rows) {
   if (!loglik_cluster_supported(p.D, p.nu)) return -1;

@@ -331,7 +331,8 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 
 template <int NB, int C>
 __global__ void __launch_bounds__(cl_warps(NB, C) * 32, 1)
-wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const LikParams p, const int ldgs, const int box_rows) {
+wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const LikParams p, const int ldgs, const int box_rows,
+                              const double* Gc, const int n0, const int nc) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(128) double sm[];
   const int D = p.D, nu = p.nu, R = D * nu, N = p.N;
@@ -361,8 +362,7 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
   const int oC = swz(gid, 2 * tig);
   // per-cluster global slot: G (D rows of pitch ldgs: this sample's A o (fmean + sqrt(fvar) o eps)), then U1, U2
   // (sample sums of Gbar, Gbar o eps)
-  double* Gs = p.ws + (long long)cid * p.ws_stride;
-  double* U1 = Gs + (long long)D * ldgs;
+  double* U1 = p.ws + (long long)cid * p.ws_stride;
   double* U2 = U1 + R;
   const uint32_t pan_u32 = smem_u32(pan);
   const uint32_t full_bar = smem_u32(sm + L.off_bar), empty_bar = full_bar + 8 * CL_MAXST;
@@ -389,17 +389,17 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
   }
   // panel g (sequence number over the kernel's lifetime) into its ring stage; issued by thread 0 only
-  auto issue_panel = [&](uint32_t g, int k0) {
+  auto issue_panel = [&](uint32_t g, int k0, int z) {
     const uint32_t stage = g % ST, round = g / ST;
     if (round > 0) cl_mbar_wait(empty_bar + 8 * stage, (round & 1u) ^ 1u);
     cl_mbar_expect_tx(full_bar + 8 * stage, (uint32_t)(STAGE * 8));
     for (int r0 = 0; r0 < Dm; r0 += box_rows)
-      cl_tma_load_3d(pan_u32 + (stage * STAGE + r0 * CL_PC) * 8, &tmG, full_bar + 8 * stage, k0, r0, cid);
+      cl_tma_load_3d(pan_u32 + (stage * STAGE + r0 * CL_PC) * 8, &tmG, full_bar + 8 * stage, k0, r0, z);
   };
   double glam_acc[2] = {0.0, 0.0};  // CTA 0, thread tid: d = tid and d = tid + 256
   cluster.sync();                   // every CTA of the cluster is resident before any remote access
 
-  for (int n = cid; n < N; n += ncl) {
+  for (int n = n0 + cid; n < n0 + nc; n += ncl) {
     const double* fm = p.fmean + (long long)n * p.ldf;
     const double* fv = p.fvar + (long long)n * p.ldf;
     for (int d = tid; d < Dp; d += blockDim.x) yv[d] = d < D ? p.y[(long long)n * D + d] : 0.0;
@@ -421,33 +421,10 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
           }
         }
       }
-      // ---------------- P0. G = A o (fmean + sqrt(fvar) o eps) of this sample into the cluster's slot ----------------
-      constexpr int GF = 8;
-      for (int base = gtid; base < R; base += GF * CT) {   // GF elements per thread in flight (coalesced over the cluster)
-        double a4[GF], f4[GF], v4[GF], e4[GF];
-#pragma unroll
-        for (int u = 0; u < GF; ++u) {
-          const int r = base + u * CT;
-          if (r < R) {
-            a4[u] = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + r % nu);
-            f4[u] = fm[r];
-            v4[u] = fv[r];
-            e4[u] = __ldg(ep + r);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < GF; ++u) {
-          const int r = base + u * CT;
-          if (r < R) {
-            const int d = r / nu, k = r - d * nu;
-            const double sd = v4[u] > 0.0 ? v4[u] * rsqrt(v4[u]) : 0.0;   // inline (sqrt() keeps a slow-path call: spills)
-            const double gm = a4[u] * f4[u], gs = a4[u] * sd;
-            Gs[d * ldgs + k] = gm + gs * e4[u];
-          }
-        }
-      }
-      __threadfence();
-      asm volatile("fence.proxy.async;" ::: "memory");   // generic writes (G, the row-sum scratch) before the TMA reads / writes
+      // G of this (sample, time step): slab zs of the chunk filled by wishart_g_fill_kernel
+      const int zs = s * nc + (n - n0);
+      const double* Gs = Gc + (long long)zs * D * ldgs;
+      asm volatile("fence.proxy.async;" ::: "memory");   // generic writes to the ring (row-sum scratch) before the TMA writes
       cluster.sync();
       // ---------------- P1. Sigma tiles = G G^T ----------------
       for (int mbase = 0; mbase < nmac; mbase += CW * CL_MQ) {
@@ -469,13 +446,13 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
             for (int v = 0; v < 2; ++v) acc[q][u][v][0] = acc[q][u][v][1] = 0.0;
         }
         if (tid == 0) {
-          for (int j = 0; j < ST - 1 && j < npan; ++j) issue_panel(pbase + j, CL_PC * j);
+          for (int j = 0; j < ST - 1 && j < npan; ++j) issue_panel(pbase + j, CL_PC * j, zs);
         }
         for (int pi = 0; pi < npan; ++pi) {
           const uint32_t g = pbase + pi, stage = g % ST;
           cl_mbar_wait(full_bar + 8 * stage, (g / ST) & 1u);
           // refill the stage every warp released one k-step ago
-          if (tid == 0 && pi + ST - 1 < npan) issue_panel(g + ST - 1, CL_PC * (pi + ST - 1));
+          if (tid == 0 && pi + ST - 1 < npan) issue_panel(g + ST - 1, CL_PC * (pi + ST - 1), zs);
           const double* P = pan + stage * STAGE;
 #pragma unroll
           for (int q = 0; q < CL_MQ; ++q) {
@@ -718,16 +695,21 @@ wishart_loglik_cluster_kernel(const __grid_constant__ CUtensorMap tmG, const Lik
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int d = tid + h * CL_WARPS * 32;
-      if (d < D) p.glam_part[(long long)cid * D + d] = glam_acc[h];
+      if (d < D) {   // per-cluster partial, accumulated over the chunks in launch order
+        const long long o = (long long)cid * D + d;
+        p.glam_part[o] = (n0 == 0 ? 0.0 : p.glam_part[o]) + glam_acc[h];
+      }
     }
   }
 }
 
-// per-cluster slot: G (D rows of pitch ldgs = nu rounded up to 4: 32-byte aligned rows for the tensor map), U1, U2
-inline long long cluster_slot_doubles(int D, int nu) {
-  const long long ldgs = (nu + 3) & ~3;
-  return ((long long)D * ldgs + 2LL * D * nu + 1) & ~1LL;
-}
+// Scratch layout: [U1, U2 slots: 2 R doubles per cluster, at most sms / 2 clusters][G of one chunk of time steps: (S, nc, D)
+// rows of pitch ldgs = nu rounded up to 4 (32-byte aligned rows for the tensor map)], filled by wishart_g_fill_kernel.  The
+// chunk budget is 8 samples x one time step per cluster of two; other sample counts get proportionally more / fewer.
+inline long long cluster_slot_doubles(int D, int nu) { return 2LL * D * nu; }
+inline long long cluster_gchunk_doubles(int D, int nu, int sms) { return 8LL * (sms / 2) * D * ((nu + 3) & ~3); }
+
+
 
 
 typedef CUresult (*ClEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -776,23 +758,39 @@ int launch_cluster_nb(const LikParams& p, cudaStream_t stream, int* part_rows) {
   if (ncl > sms / C) ncl = sms / C;
   if (ncl > p.N) ncl = p.N;
   cfg.gridDim = dim3((unsigned)(ncl * C), 1, 1);
-  // tensor map over the G slots of all clusters: (nu columns, D rows, ncl slots); a box is 4 columns x box_rows rows of
-  // one slot, rows >= D and columns >= nu are zero-filled by the copy engine
+  // chunks of time steps: G of a chunk is filled by the streaming kernel, then the persistent cluster kernel walks it
+  const int ldgs = (p.nu + 3) & ~3;
+  const long long slab = (long long)p.D * ldgs;
+  long long NC = cluster_gchunk_doubles(p.D, p.nu, sms) / (slab * p.S);
+  if (NC < 1) return FCEST_ERR_UNSUPPORTED;
+  if (NC > p.N) NC = p.N;
+  if (ncl > NC) ncl = (int)NC;                  // the same clusters (partial rows) in every chunk
+  NC = NC / ncl * ncl;                          // whole rounds of the persistent clusters per chunk (no tail inside a chunk)
+  cfg.gridDim = dim3((unsigned)(ncl * C), 1, 1);
+  double* Gc = p.ws + 2LL * p.D * p.nu * (sms / 2);
+  // tensor map over the chunk's G: (nu columns, D rows, S x NC slabs); a box is 4 columns x box_rows rows of one slab,
+  // rows >= D and columns >= nu are zero-filled by the copy engine
   ClEncodeTiledFn enc = cl_encode_fn();
   if (!enc) return FCEST_ERR_UNSUPPORTED;
-  const int ldgs = (p.nu + 3) & ~3;
   const int box_rows = L.Dm > 256 ? L.Dm / 2 : L.Dm;
   CUtensorMap tm;
-  const cuuint64_t dims[3] = {(cuuint64_t)p.nu, (cuuint64_t)p.D, (cuuint64_t)ncl};
-  const cuuint64_t strides[2] = {(cuuint64_t)ldgs * 8, (cuuint64_t)p.ws_stride * 8};
+  const cuuint64_t dims[3] = {(cuuint64_t)p.nu, (cuuint64_t)p.D, (cuuint64_t)(p.S * NC)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldgs * 8, (cuuint64_t)slab * 8};
   const cuuint32_t box[3] = {(cuuint32_t)CL_PC, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)p.ws, dims, strides, box, estr,
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)Gc, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return FCEST_ERR_ARGUMENT;
-  e = cudaLaunchKernelEx(&cfg, kern, tm, p, ldgs, box_rows);
-  if (e != cudaSuccess) return (int)e;
+  for (int n0 = 0; n0 < p.N; n0 += (int)NC) {
+    const int nc = p.N - n0 < NC ? p.N - n0 : (int)NC;
+    const int rc = launch_loglik_g_fill(p, n0, nc, ldgs, Gc, stream);
+    if (rc) return rc;
+    const double* Gcc = Gc;
+    e = cudaLaunchKernelEx(&cfg, kern, tm, p, ldgs, box_rows, Gcc, n0, nc);
+    if (e != cudaSuccess) return (int)e;
+    if (n0 + nc < p.N) FCEST_CHECK_LAUNCH();   // the caller counts / checks the last launch
+  }
   *part_rows = ncl;
   return 0;
 }

@@ -575,6 +575,13 @@ __global__ void __launch_bounds__(256) wishart_g_fill_kernel(const LikParams p, 
   }
 }
 
+int launch_loglik_g_fill(const LikParams& p, int n0, int nc, int ldgs, double* Gc, cudaStream_t stream) {
+  const int R = p.D * p.nu;
+  wishart_g_fill_kernel<<<dim3((R + 1023) / 1024, p.S * nc), 256, 0, stream>>>(p, n0, nc, ldgs, Gc);
+  FCEST_CHECK_LAUNCH();
+  return 0;
+}
+
 typedef CUresult (*LtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -605,6 +612,7 @@ static int launch_tiles_nb(const LikParams& p, cudaStream_t stream, int* part_ro
   if (NC < 1) return FCEST_ERR_UNSUPPORTED;                                    // S > 8 sms samples
   if (NC > p.N) NC = p.N;
   const int grid = (int)(NC < sms ? NC : sms);                                 // the same CTAs (partial rows) in every chunk
+  NC = NC / grid * grid;                                                       // whole rounds of the persistent CTAs per chunk
   double* Gc = p.ws + 2LL * p.D * p.nu * sms;
   // tensor map over the chunk's G: (nu columns, D rows, S x NC slabs); a box is one panel = 4 columns x Dm rows of one
   // slab, rows >= D and columns >= nu are zero-filled by the copy engine
@@ -619,11 +627,10 @@ static int launch_tiles_nb(const LikParams& p, cudaStream_t stream, int* part_ro
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return FCEST_ERR_ARGUMENT;
-  const int R = p.D * p.nu;
   for (int n0 = 0; n0 < p.N; n0 += (int)NC) {
     const int nc = p.N - n0 < NC ? p.N - n0 : (int)NC;
-    wishart_g_fill_kernel<<<dim3((R + 1023) / 1024, p.S * nc), 256, 0, stream>>>(p, n0, nc, ldgs, Gc);
-    FCEST_CHECK_LAUNCH();
+    const int rc = launch_loglik_g_fill(p, n0, nc, ldgs, Gc, stream);
+    if (rc) return rc;
     kern<<<grid, lt_warps(NB) * 32, smem, stream>>>(tm, p, ldgs, Gc, n0, nc);
     if (n0 + nc < p.N) FCEST_CHECK_LAUNCH();   // the caller counts / checks the last launch
   }

@@ -41,7 +41,7 @@ typedef struct CUstream_st* cudaStream_t;
  *   scratch : fcest_wishart_loglik_scratch_bytes(D, nu) bytes of global memory: 0 / NULL for D <= 55 (warp-per-
  *             matrix kernel); for 56 <= D <= 207 (shared-memory-tiled kernel) the per-CTA sample-sum slots plus G of one
  *             chunk of time steps (8 samples x one time step per SM); for 208 <= D <= 407 (cluster-tiled kernel) the
- *             per-cluster G / sample-sum slots.
+ *             per-cluster sample-sum slots plus G of one chunk (8 samples x one time step per pair of SMs).
  *   ws_gA_part / ws_glam_part hold per-CTA (or per-time-step) partial sums that the call reduces in fixed order. */
 long long fcest_wishart_loglik_smem_bytes(int D, int nu);
 long long fcest_wishart_loglik_scratch_bytes(int D, int nu);
