@@ -13,7 +13,9 @@
 //   * tile (ib, jb) of the lower triangle lives in the shared memory of CTA  ib mod C  (block rows dealt cyclically,
 //     packed per CTA); every CTA reaches every tile through the cluster's shared-memory window (generic pointers from
 //     `mapa`), so all DMMA operands of the O(D^3) phases come from on-chip memory of the cluster;
-//   * P0  per sample: G = A o (fmean + sqrt(fvar) o eps) once, coalesced, into the cluster's global slot (L2 resident);
+//   * P0  (separate streaming kernel, per chunk of time steps: wishart_g_fill_kernel in likelihood_tiles.cu) G = A o (fmean +
+//         sqrt(fvar) o eps) for all samples of the chunk, written once at HBM speed (a fill inside the persistent kernel was
+//         16 % of its time);
 //   * P1  Sigma = G G^T: output-stationary 16 x 16 macro tiles in registers, dealt over the cluster's warps; G arrives as
 //         4-column panels (one DMMA k-step; dense 32-byte rows are conflict-free for the fragment reads) through a ring
 //         of TMA tensor-map copies (`cp.async.bulk.tensor.3d`, SASS UTMALDG; rows >= D zero-filled by the copy engine)
