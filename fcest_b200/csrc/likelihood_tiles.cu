@@ -554,30 +554,41 @@ long long loglik_tiles_scratch_bytes(int D, int nu) {
   return (long long)sizeof(double) * (2LL * D * nu * sms + tiles_gchunk_doubles(D, nu, sms));
 }
 
-// G = A o (fmean + sqrt(fvar) o eps) for the samples / time steps of one chunk: slab z = s nc + (n - n0), D rows of pitch ldgs
+// G = A o (fmean + sqrt(fvar) o eps) for the samples / time steps of one chunk: slab z = s nc + (n - n0), D rows of pitch ldgs.
+// One thread per element (d, k) of a time step: A o fmean and A o sqrt(fvar) once, then one fused multiply-add and one
+// streaming load / store per sample (the square root per (sample, element) made the first version compute bound).
 __global__ void __launch_bounds__(256) wishart_g_fill_kernel(const LikParams p, const int n0, const int nc, const int ldgs,
                                                              double* __restrict__ Gc) {
   const int R = p.D * p.nu;
-  const int z = blockIdx.y, s = z / nc, n = n0 + (z - s * nc);
+  const int i = blockIdx.y, n = n0 + i;
   const double* fm = p.fmean + (long long)n * p.ldf;
   const double* fv = p.fvar + (long long)n * p.ldf;
-  const double* ep = p.eps + ((long long)s * p.N + n) * R;
-  double* G = Gc + (long long)z * p.D * ldgs;
+  const long long slab = (long long)p.D * ldgs;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int r = (blockIdx.x * 4 + u) * 256 + threadIdx.x;
+  for (int u = 0; u < 2; ++u) {
+    const int r = (blockIdx.x * 2 + u) * 256 + threadIdx.x;
     if (r < R) {
       const int d = r / p.nu, k = r - d * p.nu;
       const double a = p.a_mode == 0 ? __ldg(p.A + r) : __ldg(p.A + k);
       const double gm = a * fm[r], gs = a * sqrt(fv[r]);
-      G[d * ldgs + k] = gm + gs * __ldg(ep + r);
+      const double* ep = p.eps + (long long)n * R + r;
+      double* G = Gc + (long long)i * slab + d * ldgs + k;
+      int s = 0;
+      for (; s + 4 <= p.S; s += 4) {   // four samples in flight
+        double e[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[q] = __ldg(ep + (long long)(s + q) * p.N * R);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) G[(long long)(s + q) * nc * slab] = gm + gs * e[q];
+      }
+      for (; s < p.S; ++s) G[(long long)s * nc * slab] = gm + gs * __ldg(ep + (long long)s * p.N * R);
     }
   }
 }
 
 int launch_loglik_g_fill(const LikParams& p, int n0, int nc, int ldgs, double* Gc, cudaStream_t stream) {
   const int R = p.D * p.nu;
-  wishart_g_fill_kernel<<<dim3((R + 1023) / 1024, p.S * nc), 256, 0, stream>>>(p, n0, nc, ldgs, Gc);
+  wishart_g_fill_kernel<<<dim3((R + 511) / 512, nc), 256, 0, stream>>>(p, n0, nc, ldgs, Gc);
   FCEST_CHECK_LAUNCH();
   return 0;
 }
