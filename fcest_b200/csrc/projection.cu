@@ -433,6 +433,9 @@ tri_stationary_kernel(const double* __restrict__ q_sqrt, int M, const double* __
 // pattern [gid][tig + 4h] then touches every bank pair once per half-warp.
 // ---------------------------------------------------------------------------------------------
 constexpr int TSM_WARPS = 32;
+// threads per CTA of the resident-factor kernels: a 50 x 50 factor (C5: 40 000 latents) has ~10 work units, so 8 warps and
+// four or more CTAs per SM; 32 warps from M = 129 (the factor fills the shared memory of an SM at M = 200)
+static inline int tsm_threads(int M) { return M <= 64 ? 256 : (M <= 128 ? 512 : TSM_WARPS * 32); }
 
 __device__ __forceinline__ int tsm_off(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
 
@@ -448,7 +451,8 @@ tri_syrk_smem_kernel(const double* __restrict__ q_sqrt, int M, double* __restric
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   // ---- copy the lower blocks in: one warp per row, lanes over the 16-byte chunks of columns [0, 8 (ib + 1))
-  for (int i = warp; i < Mp; i += TSM_WARPS) {
+  const int nwarps = blockDim.x >> 5;   // 32 warps at M = 200; fewer for small factors (several CTAs per SM)
+  for (int i = warp; i < Mp; i += nwarps) {
     const int ib = i >> 3, r = i & 7;
     double* brow = Lb + (size_t)(ib * (ib + 1) / 2) * 64;
     for (int col = 2 * lane; col < 8 * (ib + 1); col += 64) {
@@ -485,9 +489,9 @@ tri_syrk_smem_kernel(const double* __restrict__ q_sqrt, int M, double* __restric
     units[u] = (unsigned short)(((j + rem) << 8) | j);
   }
   __syncthreads();
-  for (int round = 0; round * TSM_WARPS < nunits; ++round) {
+  for (int round = 0; round * nwarps < nunits; ++round) {
     {
-      const int idx = round * TSM_WARPS + ((round & 1) ? TSM_WARPS - 1 - warp : warp);
+      const int idx = round * nwarps + ((round & 1) ? nwarps - 1 - warp : warp);
       if (idx >= nunits) continue;
       const int ib = units[idx] >> 8, jb0 = units[idx] & 255;
       const bool two = jb0 + 1 <= ib;
@@ -557,7 +561,8 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
   double* __restrict__ dq = dq_sqrt + (long long)r_lat * M * M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  for (int i = warp; i < Mp; i += TSM_WARPS) {   // resident lower blocks of L (see tri_syrk_smem_kernel)
+  const int nwarps = blockDim.x >> 5;
+  for (int i = warp; i < Mp; i += nwarps) {   // resident lower blocks of L (see tri_syrk_smem_kernel)
     const int ib = i >> 3, r = i & 7;
     double* brow = Lb + (size_t)(ib * (ib + 1) / 2) * 64;
     for (int col = 2 * lane; col < 8 * (ib + 1); col += 64) {
@@ -569,7 +574,7 @@ tri_grad_smem_kernel(const double* __restrict__ Gk, long long ldk, const double*
   cp_async_commit();
   // strict upper triangle of dq_sqrt is zero (under the copy); the fused optimiser never touches it
   if (!ADAM) {
-    for (int i = warp; i < M; i += TSM_WARPS)
+    for (int i = warp; i < M; i += nwarps)
       for (int j = i + 1 + lane; j < M; j += 32) dq[(long long)i * M + j] = 0.0;
   }
   // unit table: block rows from the bottom, groups of TG_NC column blocks left to right (heavy first within a row);
@@ -765,7 +770,7 @@ extern "C" int fcest_tri_syrk_pack(const double* q_sqrt, int R, int M, double* S
     const size_t smem = sizeof(double) * 64 * (size_t)(nb * (nb + 1) / 2);
     cudaError_t e = cudaFuncSetAttribute(tri_syrk_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    tri_syrk_smem_kernel<<<R, TSM_WARPS * 32, smem, stream>>>(q_sqrt, M, Sk, ldk, kl_parts);
+    tri_syrk_smem_kernel<<<R, tsm_threads(M), smem, stream>>>(q_sqrt, M, Sk, ldk, kl_parts);
     FCEST_CHECK_LAUNCH();
     return 0;
   }
@@ -798,7 +803,7 @@ extern "C" int fcest_tri_grad(const double* Gk, long long ldk, const double* q_s
     const size_t smem = sizeof(double) * 64 * (size_t)(nb * (nb + 1) / 2);
     cudaError_t e = cudaFuncSetAttribute(tri_grad_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    tri_grad_smem_kernel<false><<<R, TSM_WARPS * 32, smem, stream>>>(Gk, ldk, q_sqrt, M, dq_sqrt, kl, TriAdam());
+    tri_grad_smem_kernel<false><<<R, tsm_threads(M), smem, stream>>>(Gk, ldk, q_sqrt, M, dq_sqrt, kl, TriAdam());
     FCEST_CHECK_LAUNCH();
     return 0;
   }
@@ -829,7 +834,7 @@ extern "C" int fcest_tri_grad_adam(const double* Gk, long long ldk, double* q_sq
     if (e2 != cudaSuccess) return (int)e2;
     TriAdam ad2;
     ad2.m = m; ad2.v = v; ad2.alpha_dev = alpha_t; ad2.b1 = b1; ad2.b2 = b2; ad2.eps = eps;
-    tri_grad_smem_kernel<true><<<R, TSM_WARPS * 32, smem_r, stream>>>(Gk, ldk, q_sqrt, M, nullptr, kl, ad2);
+    tri_grad_smem_kernel<true><<<R, tsm_threads(M), smem_r, stream>>>(Gk, ldk, q_sqrt, M, nullptr, kl, ad2);
     FCEST_CHECK_LAUNCH();
     return 0;
   }
