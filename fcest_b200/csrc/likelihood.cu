@@ -294,7 +294,11 @@ static const int kBigCtas = 148 * 3;
 extern "C" long long fcest_wishart_loglik_scratch_bytes(int D, int nu) {
   long long need = 0;
   if (!loglik_warp_supported(D, nu) && loglik_tiles_supported(D, nu)) need = loglik_tiles_scratch_bytes(D, nu);
-  if (loglik_cluster_supported(D, nu) && loglik_cluster_scratch_bytes(D, nu) > need) need = loglik_cluster_scratch_bytes(D, nu);
+  // the cluster-tiled kernel serves the sizes neither of the above takes (and any size under FCEST_LIK_IMPL=cluster)
+  static const bool force_cluster_scr = [] { const char* v = getenv("FCEST_LIK_IMPL"); return v && !strcmp(v, "cluster"); }();
+  if ((force_cluster_scr || (!loglik_warp_supported(D, nu) && !loglik_tiles_supported(D, nu))) && loglik_cluster_supported(D, nu) &&
+      loglik_cluster_scratch_bytes(D, nu) > need)
+    need = loglik_cluster_scratch_bytes(D, nu);
   if (fcest_wishart_loglik_smem_bytes(D, nu) > 227 * 1024) {
     const int Dp = (D + 7) / 8 * 8, Np = (nu + 7) / 8 * 8;
     const long long stride = (long long)Dp * pitch4(Np) + (long long)Dp * pitch4(Dp) + 12LL * Dp;

@@ -73,3 +73,26 @@ def test_synthetic_inputs_equal_the_checker_inputs():
         assert np.array_equal(s["eps"], eps.numpy())
         for k in ("Z", "q_mu", "q_sqrt", "A", "lam"):
             assert np.array_equal(s[k], p[k].numpy()), k
+
+
+def test_likelihood_scratch_sizes_follow_the_kernel_choice():
+    """`fcest_wishart_loglik_scratch_bytes` is a pure size computation (no launch): nothing for the warp-per-matrix kernel
+    (D <= 55), sample-sum slots + one G chunk for the shared-memory-tiled kernel (56 .. 207) and for the cluster-tiled
+    kernel (208 .. 407).  Without a device the library assumes 148 SMs."""
+    from fcest_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    f = lib.fcest_wishart_loglik_scratch_bytes
+    f.restype = ctypes.c_longlong
+    f.argtypes = [ctypes.c_int, ctypes.c_int]
+    assert f(50, 50) == 0 and f(15, 15) == 0
+    sms = 148
+    for D in (64, 100, 200):                      # tiles kernel: [2 R doubles per CTA][8 samples x sms time steps of G]
+        ldgs = (D + 3) // 4 * 4
+        assert f(D, D) == 8 * (2 * D * D * sms + 8 * sms * D * ldgs), D
+    for D in (232, 256, 400):                     # cluster-tiled kernel: slots for sms / 2 clusters; the L2-scratch kernel's
+        ldgs = (D + 3) // 4 * 4                   # buffer (kept for FCEST_LIK_IMPL=cta) is the larger of the two
+        need = 8 * (2 * D * D * (sms // 2) + 8 * (sms // 2) * D * ldgs)
+        assert f(D, D) >= need, D
+    assert f(64, 64) < f(100, 100) < f(200, 200)
